@@ -1,0 +1,207 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules
+(/root/reference/model/{lidar4d,renderer,planes_field,hash_field,flow_field}.py)
+on top of oracle/tcnn_shim.py, and pin oracle/lidar4d_oracle.py against them.
+
+Run in the build container only (needs /root/reference, read-only):
+    python tests/golden/make_golden.py
+The fixtures it writes are small (reduced table sizes) and committed; the GPU
+box only ever reads the .npz files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+REF = "/root/reference"
+
+from oracle import tcnn_shim  # noqa: E402
+from oracle import lidar4d_oracle as O  # noqa: E402
+from lidar4d_b200.geometry import FieldConfig, make_frame  # noqa: E402
+from lidar4d_b200.rays import lidar_rays  # noqa: E402
+
+# small-table configuration: same structure, tables shrunk so fixtures stay small
+SMALL = dict(min_resolution=8, base_resolution=16, max_resolution=512, time_resolution=8,
+             n_levels_hash=4, log2_hashmap_size=12, num_frames=6,
+             near_lidar=0.0105, far_lidar=0.851)
+SMALL_DYN = (9, 8, 8)
+SMALL_FLOW = dict(base_resolution=8, max_resolution=256, log2_hashmap_size=10)
+
+
+def build_reference(cfg_kw):
+    tcnn_shim.install()
+    sys.path.insert(0, REF)
+    import model.hash_field as hf
+    import model.flow_field as ff
+    import model.lidar4d as l4d
+
+    # The reference hard-codes the dynamic hash sizes and the flow grid sizes as
+    # keyword defaults (hash_field.py:100, flow_field.py:50-54).  Shrink them
+    # through the constructors' own keyword arguments, not by editing code.
+    class SmallHash(hf.HashGrid4D):
+        def __init__(self, **kw):
+            super().__init__(hash_size_dynamic=list(SMALL_DYN), **kw)
+
+    class SmallFlow(ff.FlowField):
+        def __init__(self, **kw):
+            super().__init__(**SMALL_FLOW, **kw)
+
+    l4d.HashGrid4D = SmallHash
+    l4d.FlowField = SmallFlow
+    kw = {k: v for k, v in cfg_kw.items()}
+    model = l4d.LiDAR4D(**kw)
+    return model
+
+
+def small_config(cfg_kw=SMALL):
+    return FieldConfig(**cfg_kw, hash_size_dynamic=SMALL_DYN,
+                      flow_base_resolution=SMALL_FLOW["base_resolution"],
+                      flow_max_resolution=SMALL_FLOW["max_resolution"],
+                      flow_log2_hashmap_size=SMALL_FLOW["log2_hashmap_size"])
+
+
+def oracle_for(cfg_kw, seed):
+    return O.build_seeded(small_config(cfg_kw), seed, flow_last_std=0.02)
+
+
+def to_np(d):
+    return {k: v.detach().cpu().numpy() for k, v in d.items()}
+
+
+def run_case(name, time, n_rays_hw, num_steps, perturb, seed):
+    orc = oracle_for(SMALL, seed)
+    ref = build_reference(SMALL)
+    sd = orc.ref_state_dict()
+    missing = ref.load_state_dict(sd, strict=False)
+    assert all(k.startswith("unet") for k in missing.missing_keys), missing
+    assert not missing.unexpected_keys, missing
+
+    H, W = n_rays_hw
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, 3] = [0.1, -0.05, 0.02]
+    ro, rd = lidar_rays(pose, H, W, fov_up=2.0, fov=26.9)
+    rays_o = torch.from_numpy(ro)[None]
+    rays_d = torch.from_numpy(rd)[None]
+    t = torch.tensor([[time]], dtype=torch.float32)
+    N = H * W
+
+    # the reference draws jitter from torch.rand (renderer.py:84): feed it the
+    # repo's counter-based stream so the perturbed case is reproducible
+    orig_rand = torch.rand
+    if perturb:
+        u = torch.from_numpy(O.jitter_uniform(seed, np.arange(N), num_steps))
+        torch.rand = lambda *a, **k: u.clone()
+    try:
+        out_ref = ref.render(rays_o, rays_d, t, staged=False, num_steps=num_steps, perturb=perturb)
+    finally:
+        torch.rand = orig_rand
+    g_depth = torch.linspace(0.5, 1.5, N).view(1, N)
+    g_image = torch.stack([torch.linspace(-1, 1, N), torch.linspace(1, 0.2, N)], -1).view(1, N, 2)
+    loss = (out_ref["depth_lidar"] * g_depth).sum() + (out_ref["image_lidar"] * g_image).sum()
+    loss.backward()
+    ref_grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p))
+                 for k, p in ref.named_parameters() if not k.startswith("unet")}
+
+    # the reference's z grid comes from the CPU torch.linspace; hand the oracle
+    # the identical grid so this comparison isolates the model arithmetic
+    lin = torch.linspace(0.0, 1.0, num_steps).numpy()
+    out_orc = orc.render(rays_o[0], rays_d[0], time, num_steps=num_steps, perturb=perturb, seed=seed,
+                         lin=lin, return_stages=True)
+    loss_o = (out_orc["depth_lidar"] * g_depth[0]).sum() + (out_orc["image_lidar"] * g_image[0]).sum()
+    loss_o.backward()
+    orc_grads = orc.ref_named_grads()
+
+    def rel(a, b):
+        a, b = a.detach().double().reshape(-1), b.detach().double().reshape(-1)
+        if a.numel() == 0:
+            return 0.0
+        return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+    report = {}
+    for k in ["depth_lidar", "image_lidar", "weights_sum_lidar", "weights", "z_vals"]:
+        report[k] = rel(out_orc[k].reshape(-1), out_ref[k].reshape(-1))
+    for k, g in ref_grads.items():
+        report["grad:" + k] = rel(orc_grads[k], g)
+    worst = max(report.values())
+    print(f"[{name}] oracle vs reference-on-shim: worst rel-to-max err {worst:.3e}")
+    for k, v in sorted(report.items(), key=lambda kv: -kv[1])[:6]:
+        print(f"     {k:60s} {v:.3e}")
+    assert worst < 2e-5, "oracle does not reproduce the reference code"
+
+    # also flow() (lidar4d.py:124-137)
+    pts = (torch.rand(257, 3, generator=torch.Generator().manual_seed(seed + 1)) * 2 - 1)
+    fl_ref = ref.flow(pts, t)
+    fl_orc = orc.flow(pts, time)
+    for k in ("forward", "backward"):
+        assert rel(fl_orc[k], fl_ref[k]) < 1e-5
+
+    fx = {
+        "time": np.float32(time), "H": H, "W": W, "num_steps": num_steps, "perturb": int(perturb),
+        "seed": seed, "rays_o": ro, "rays_d": rd, "pose": pose,
+        "g_depth": g_depth[0].numpy(), "g_image": g_image[0].numpy(),
+        "flow_pts": pts.numpy(), "flow_forward": fl_ref["forward"].detach().numpy(),
+        "flow_backward": fl_ref["backward"].detach().numpy(),
+    }
+    for k in ["depth_lidar", "image_lidar", "weights_sum_lidar"]:
+        fx["ref_" + k] = out_ref[k].detach().numpy().reshape(-1) if k != "image_lidar" \
+            else out_ref[k].detach().numpy().reshape(-1, 2)
+    fx["ref_weights"] = out_ref["weights"].detach().numpy().astype(np.float32)
+    # compact gradient fingerprints: per-parameter L2 norm and a fixed random projection
+    rng = np.random.default_rng(1234)
+    for k, g in ref_grads.items():
+        gv = g.double().numpy().reshape(-1)
+        proj = rng.standard_normal(gv.shape[0])
+        fx["gradnorm:" + k] = np.float64(np.linalg.norm(gv))
+        fx["gradproj:" + k] = np.float64(gv @ proj)
+    small = {k: v for k, v in ref_grads.items() if v.numel() <= 12000}
+    for k, g in small.items():
+        fx["grad:" + k] = g.numpy().astype(np.float32)
+    # the parameters themselves are regenerated from the seed by
+    # oracle.randomize_parameters; store a checksum so drift is detected
+    fx["param_checksum"] = np.float64(sum(float(v.double().sum()) for v in sd.values()))
+    out_path = os.path.join(ROOT, "tests", "golden", f"{name}.npz")
+    np.savez_compressed(out_path, **fx)
+    print(f"     wrote {out_path} ({os.path.getsize(out_path)/1024:.1f} KiB)")
+
+
+def hash_index_vectors():
+    """Known-answer uint32 hash indices for fixed points at every level of the
+    three grid types (3D hashed, 2D hashed, 3D with a dense level 0), incl. edge
+    coordinates {0, 1, 1-eps, <0, >1}."""
+    cfg = FieldConfig()
+    grids = {"static3d": cfg.static_grid(), "dyn2d_xy": cfg.dynamic_grid(0),
+             "dyn2d_xz": cfg.dynamic_grid(1), "flow3d": cfg.flow_grid()}
+    g = torch.Generator().manual_seed(7)
+    fx = {}
+    for name, geo in grids.items():
+        D = geo.n_dims
+        x = torch.rand(64, D, generator=g)
+        edge = torch.tensor([[0.0] * D, [1.0] * D, [1.0 - 2 ** -24] * D, [-0.013] * D, [1.021] * D,
+                             [0.5] * D, [-1.7] * D])
+        x = torch.cat([x, edge], 0)
+        fx[name + ":x"] = x.numpy()
+        fx[name + ":scale"] = geo.scale
+        fx[name + ":resolution"] = geo.resolution
+        fx[name + ":entries"] = geo.entries
+        fx[name + ":offset"] = geo.offset
+        for l in range(geo.n_levels):
+            idx, w = O.hash_indices(x, geo, l)
+            fx[f"{name}:idx{l}"] = idx.numpy().astype(np.uint32)
+            fx[f"{name}:w{l}"] = w.numpy()
+    out_path = os.path.join(ROOT, "tests", "golden", "hash_indices.npz")
+    np.savez_compressed(out_path, **fx)
+    print(f"wrote {out_path} ({os.path.getsize(out_path)/1024:.1f} KiB)")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    hash_index_vectors()
+    # interior frame (both neighbours), perturb off
+    run_case("ref_small_interior", time=0.4, n_rays_hw=(4, 12), num_steps=48, perturb=False, seed=3)
+    # first frame (no backward neighbour), slice index integral (t*7 == 0)
+    run_case("ref_small_first", time=0.0, n_rays_hw=(3, 10), num_steps=40, perturb=False, seed=4)
+    # last frame (no forward neighbour), with jitter
+    run_case("ref_small_last", time=1.0, n_rays_hw=(3, 10), num_steps=40, perturb=True, seed=5)
