@@ -1,0 +1,359 @@
+// l4d_bwd.cuh - per-sample phases of the backward pass (host+device, see
+// l4d_core.cuh).  The reference has no backward code: it relies on autograd
+// over model/renderer.py:98-129 and model/lidar4d.py:139-223; SURVEY.md
+// Appendix A.12 derives what is restated here.
+//
+// Data flow of one tile of NT samples (thread == sample).  "TA"/"TB" are
+// shared-memory tiles [NT][LD] in which every thread owns one row; between the
+// phases the block runs cooperative outer products  dW += TA^T * TB  (device:
+// l4d_kernels.cu; host: plain loops in tests/hostsim).
+//
+//   B0  flow MLP recompute from saved flow_in           -> flow[6], relu masks
+//   B1  sigma MLP recompute from saved features         -> h0, geo, relu mask, hidden (scratch)
+//   B2  per attribute net: recompute + backprop         -> dW tiles, dgeo
+//   B3  sigma MLP backprop                              -> dW tiles, dh[64]
+//   B4  scatter dh through the encoders                 -> table / plane REDs, dflow
+//   B5  flow MLP backprop + flow-grid scatter
+#pragma once
+#include "l4d_core.cuh"
+
+#define L4D_TILE_LD 68     // tile leading dimension: 64 + 4 keeps float4 alignment
+
+struct BwSample {
+  bool active;             // sample index < n_steps
+  bool masked;             // w > 1e-4
+  float x, y, z;           // position in [0,1]^3
+  float flow[8];
+  uint32_t mf1a, mf1b, mf2a, mf2b;   // flow MLP relu patterns
+  uint32_t msa, msb;                 // sigma hidden relu pattern
+  float h0;                          // pre-exp sigma output
+  float geo[L4D_GEO];
+  float dsigma;                      // dL/dsigma from the compositing backward
+  float da[2];                       // dL/d(raydrop, intensity) (0 when not masked)
+  float dgeo[L4D_GEO];
+  float dh[L4D_H];                   // dL/d(sigma hidden pre-activation)
+  float dflow[6];
+};
+
+// ---- B0: flow MLP forward from the saved Lagrange-contracted inputs -------------------
+L4D_HD void l4d_bw_flow_fwd(const DevModel& M, BwSample& s, const float* flow_in, size_t stride,
+                            float* xb, int xs) {
+#pragma unroll
+  for (int k = 0; k < L4D_FLOW_IN; ++k) xb[k * xs] = s.active ? flow_in[(size_t)k * stride] : 0.f;
+  l4d_flow_mlp(M, xb, xs, s.flow, s.mf1a, s.mf1b, s.mf2a, s.mf2b);
+}
+
+// ---- B1: sigma MLP forward from the saved features --------------------------------------
+// writes relu(hidden) to xb[0..64) and to hidden_out (scratch plane, stride hs)
+L4D_HD void l4d_bw_sigma_fwd(const DevModel& M, BwSample& s, const float* feat, size_t stride,
+                             float* xb, int xs, float* hidden_out, size_t hs) {
+  float acc[L4D_H];
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) acc[k] = 0.f;
+  if (s.active) {
+    for (int k = 0; k < (int)M.sigma_in_dim; ++k) l4d_axpy64(acc, feat[(size_t)k * stride], M.sig_w1t + (size_t)k * L4D_H);
+    for (int k = (int)M.sigma_in_dim; k < (int)M.sigma_in_pad; ++k) l4d_axpy64(acc, 1.0f, M.sig_w1t + (size_t)k * L4D_H);
+  }
+  l4d_relu_store(acc, xb, xs, s.msa, s.msb);
+  if (s.active) {
+#pragma unroll
+    for (int k = 0; k < L4D_H; ++k) hidden_out[(size_t)k * hs] = xb[k * xs];
+  }
+  float out[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) out[k] = 0.f;
+  l4d_layer_small<16>(out, xb, xs, L4D_H, M.sig_w2t);
+  s.h0 = out[0];
+#pragma unroll
+  for (int k = 0; k < L4D_GEO; ++k) { s.geo[k] = out[1 + k]; s.dgeo[k] = 0.f; }
+}
+
+// ---- B2: one attribute head.  Split in three steps around the cooperative products. ----
+// step a: forward; TA row <- h1 ; TB row <- d_o * h2 (for dw3 = colsum) ; returns d_o and keeps
+//         dh2 (masked by relu2) in xb[0..64)
+L4D_HD void l4d_bw_attr_a(const DevModel& M, int net, BwSample& s, const float* cdir, float* xb, int xs,
+                          float* ta_row, float* tb_row, uint32_t& m1a, uint32_t& m1b) {
+  float y[L4D_H];
+  const bool on = s.active && s.masked;
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) y[k] = cdir[net * L4D_H + k];
+#pragma unroll
+  for (int k = 0; k < L4D_GEO; ++k) xb[k * xs] = s.geo[k];
+  l4d_layer64(y, xb, xs, L4D_GEO, M.att_w1t[net] + (size_t)L4D_ENC * L4D_H);
+  l4d_relu_store(y, xb, xs, m1a, m1b);
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) ta_row[k] = on ? xb[k * xs] : 0.f;
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) y[k] = 0.f;
+  l4d_layer64(y, xb, xs, L4D_H, M.att_w2t[net]);
+  uint32_t m2a = 0u, m2b = 0u;
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) {
+    bool p = y[k] > 0.f;
+    y[k] = p ? y[k] : 0.f;
+    if (k < 32) m2a |= p ? (1u << k) : 0u; else m2b |= p ? (1u << (k - 32)) : 0u;
+  }
+  const float a = l4d_sigmoid(l4d_dot64(y, M.att_w3[net]));
+  const float d_o = on ? s.da[net] * a * (1.0f - a) : 0.f;
+#pragma unroll
+  for (int q = 0; q < L4D_H / 4; ++q) {
+    float4 w3 = l4d_ld4(M.att_w3[net] + 4 * q);
+    const float wv[4] = {w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = 4 * q + i;
+      tb_row[k] = d_o * y[k];
+      xb[k * xs] = l4d_bit(m2a, m2b, k) ? wv[i] * d_o : 0.f;     // dh2
+    }
+  }
+}
+// step b: (after dw3 colsum) TB row <- dh2
+L4D_HD void l4d_bw_attr_b(float* xb, int xs, float* tb_row) {
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) tb_row[k] = xb[k * xs];
+}
+// step c: (after dW2t product) dh1 = (W2^T dh2) * relu1 ; TB row <- dh1 ; TA row[0..16) <- geo|0 ;
+//         dgeo += W1g^T dh1
+L4D_HD void l4d_bw_attr_c(const DevModel& M, int net, BwSample& s, float* xb, int xs,
+                          float* ta_row, float* tb_row, uint32_t m1a, uint32_t m1b) {
+  float d[L4D_H];
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) d[k] = 0.f;
+  l4d_layer64(d, xb, xs, L4D_H, M.att_w2[net]);          // native rows [o][k]: d[k] += dh2[o] W2[o][k]
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) {
+    d[k] = l4d_bit(m1a, m1b, k) ? d[k] : 0.f;
+    tb_row[k] = d[k];
+  }
+  const bool on = s.active && s.masked;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) ta_row[k] = (on && k < L4D_GEO) ? s.geo[k] : 0.f;
+#pragma unroll
+  for (int k = 0; k < L4D_GEO; ++k) s.dgeo[k] += l4d_dot64(d, M.att_w1t[net] + (size_t)(L4D_ENC + k) * L4D_H);
+}
+
+// ---- B3: sigma MLP backprop ------------------------------------------------------------
+// step a: TA row[0..16) <- dout ; TB row <- hidden (from scratch) ; xb[0..16) <- dout
+L4D_HD void l4d_bw_sigma_a(const DevModel& M, BwSample& s, const float* hidden, size_t hs, float* xb, int xs,
+                           float* ta_row, float* tb_row) {
+  // trunc_exp backward: g * exp(clamp(x,-15,15))  (activation.py:17)
+  const float d0 = s.active ? s.dsigma * expf(fminf(fmaxf(s.h0, -15.f), 15.f)) : 0.f;
+  ta_row[0] = d0;
+  xb[0] = d0;
+#pragma unroll
+  for (int k = 0; k < L4D_GEO; ++k) {
+    const float v = s.active ? s.dgeo[k] : 0.f;
+    ta_row[1 + k] = v;
+    xb[(1 + k) * xs] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) tb_row[k] = s.active ? hidden[(size_t)k * hs] : 0.f;
+}
+// step b: dh = (W2^T dout) * relu ; TB row <- dh
+L4D_HD void l4d_bw_sigma_b(const DevModel& M, BwSample& s, const float* xb, int xs, float* tb_row) {
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) s.dh[k] = 0.f;
+  l4d_layer64(s.dh, xb, xs, 16, M.sig_w2);               // native [16][64]
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) {
+    s.dh[k] = l4d_bit(s.msa, s.msb, k) ? s.dh[k] : 0.f;
+    tb_row[k] = s.dh[k];
+  }
+}
+// step c (per 64-wide chunk of the input): TA row <- features[chunk]
+L4D_HD void l4d_bw_sigma_c(const DevModel& M, const BwSample& s, const float* feat, size_t stride, int chunk,
+                           float* ta_row) {
+  for (int k = 0; k < L4D_H; ++k) {
+    const int r = chunk * L4D_H + k;
+    float v = 0.f;
+    if (s.active && r < (int)M.sigma_in_pad) v = r < (int)M.sigma_in_dim ? feat[(size_t)r * stride] : 1.0f;
+    ta_row[k] = v;
+  }
+}
+
+// ---- B4: scatter dh through the encoders ------------------------------------------------
+L4D_HD float l4d_dfeat(const DevModel& M, const BwSample& s, int row) {
+  return l4d_dot64(s.dh, M.sig_w1t + (size_t)row * L4D_H);
+}
+
+L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads& G, BwSample& s) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s.dflow[k] = 0.f;
+  if (!s.active) return;
+  const int nS = (int)M.n_scales;
+  const int L = (int)M.gs.n_levels;
+  const int row_plane_d = nS * 8;
+  const int row_hash_s = 2 * nS * 8;
+  const int row_hash_d = row_hash_s + L * 4;
+  float wc, wf, wb;
+  l4d_agg_weights(F, wc, wf, wb);
+  const float x = s.x, y = s.y, z = s.z;
+  const float xf0 = x + s.flow[0], xf1 = y + s.flow[1], xf2 = z + s.flow[2];
+  const float xw0 = x + s.flow[3], xw1 = y + s.flow[4], xw2 = z + s.flow[5];
+
+#pragma unroll 1
+  for (int sc = 0; sc < nS; ++sc) {
+    const int R = (int)M.plane_res[sc];
+    const int T = (int)M.time_res;
+    {   // static planes: product rule over (x,y) (x,z) (y,z)
+      float d[8], v0[8], v1[8], v2[8], dummy[8], g[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) d[c] = l4d_dfeat(M, s, sc * 8 + c);
+      Bilerp b0 = l4d_bilerp(x, R, y, R), b1 = l4d_bilerp(x, R, z, R), b2 = l4d_bilerp(y, R, z, R);
+      l4d_plane_sample<false>(M.planes[sc][0], R, b0, v0, dummy);
+      l4d_plane_sample<false>(M.planes[sc][1], R, b1, v1, dummy);
+      l4d_plane_sample<false>(M.planes[sc][3], R, b2, v2, dummy);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[c] = d[c] * v1[c] * v2[c];
+      l4d_plane_scatter(G.planes_cl[sc][0], R, b0, g);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[c] = d[c] * v0[c] * v2[c];
+      l4d_plane_scatter(G.planes_cl[sc][1], R, b1, g);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[c] = d[c] * v0[c] * v1[c];
+      l4d_plane_scatter(G.planes_cl[sc][3], R, b2, g);
+    }
+    {   // time planes (x,t) (y,t) (z,t): three queries, warped ones also feed d(coords) -> flow
+      float d[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) d[c] = l4d_dfeat(M, s, row_plane_d + sc * 8 + c);
+#pragma unroll 1
+      for (int qi = 0; qi < 3; ++qi) {
+        const float wq = qi == 0 ? wc : (qi == 1 ? wf : wb);
+        if (wq == 0.f) continue;
+        const float q0 = qi == 0 ? x : (qi == 1 ? xf0 : xw0);
+        const float q1 = qi == 0 ? y : (qi == 1 ? xf1 : xw1);
+        const float q2 = qi == 0 ? z : (qi == 1 ? xf2 : xw2);
+        const float tau = qi == 0 ? F.cur.tau : (qi == 1 ? F.fwd.tau : F.bwd.tau);
+        float v0[8], v1[8], v2[8], x0[8], x1[8], x2[8], g[8];
+        Bilerp b0 = l4d_bilerp(q0, R, tau, T), b1 = l4d_bilerp(q1, R, tau, T), b2 = l4d_bilerp(q2, R, tau, T);
+        l4d_plane_sample<true>(M.planes[sc][2], R, b0, v0, x0);
+        l4d_plane_sample<true>(M.planes[sc][4], R, b1, v1, x1);
+        l4d_plane_sample<true>(M.planes[sc][5], R, b2, v2, x2);
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v1[c] * v2[c]; c0 = fmaf(g[c], x0[c], c0); }
+        l4d_plane_scatter(G.planes_cl[sc][2], R, b0, g);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v0[c] * v2[c]; c1 = fmaf(g[c], x1[c], c1); }
+        l4d_plane_scatter(G.planes_cl[sc][4], R, b1, g);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v0[c] * v1[c]; c2 = fmaf(g[c], x2[c], c2); }
+        l4d_plane_scatter(G.planes_cl[sc][5], R, b2, g);
+        if (qi == 1) { s.dflow[0] += c0; s.dflow[1] += c1; s.dflow[2] += c2; }
+        if (qi == 2) { s.dflow[3] += c0; s.dflow[4] += c1; s.dflow[5] += c2; }
+      }
+    }
+  }
+
+  // static hash: dL/dtable[entry] += w_corner * dfeat[0..4)
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    uint32_t idx[8]; float w[8];
+    l4d_corners3(M.gs, l, x, y, z, idx, w);
+    const float d0 = l4d_dfeat(M, s, row_hash_s + 4 * l + 0), d1 = l4d_dfeat(M, s, row_hash_s + 4 * l + 1);
+    const float d2 = l4d_dfeat(M, s, row_hash_s + 4 * l + 2), d3 = l4d_dfeat(M, s, row_hash_s + 4 * l + 3);
+    float* base = G.hs + (size_t)M.gs.offset[l] * 4;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) l4d_red4(base + (size_t)idx[c] * 4, w[c] * d0, w[c] * d1, w[c] * d2, w[c] * d3);
+  }
+
+  // dynamic hash: only the (x,t) query carries gradient (lidar4d.py:160-161,169-170 are no_grad)
+#pragma unroll 1
+  for (int p = 0; p < 3; ++p) {
+    const float ca = p == 2 ? y : x, cb = p == 0 ? y : z;
+    float* glo = G.hd[p][F.cur.slice_lo];
+    float* ghi = G.hd[p][F.cur.slice_hi];
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+      uint32_t idx[4]; float w[4];
+      l4d_corners2(M.gd[p], l, ca, cb, idx, w);
+      const float d = wc * l4d_dfeat(M, s, row_hash_d + p * L + l);
+      const float e0 = d * F.cur.basis[0], e1 = d * F.cur.basis[1], e2 = d * F.cur.basis[2], e3 = d * F.cur.basis[3];
+      const float slo = F.cur.single ? 1.0f : F.cur.w_lo;
+      const size_t off = (size_t)M.gd[p].offset[l] * 4;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float ww = w[c] * slo;
+        l4d_red4(glo + off + (size_t)idx[c] * 4, ww * e0, ww * e1, ww * e2, ww * e3);
+      }
+      if (!F.cur.single) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float ww = w[c] * F.cur.w_hi;
+          l4d_red4(ghi + off + (size_t)idx[c] * 4, ww * e0, ww * e1, ww * e2, ww * e3);
+        }
+      }
+    }
+  }
+}
+
+// ---- B5: flow MLP backprop.  g[6] = dL/dflow of this sample. ----------------------------
+// step a: recompute h1,h2 ; TA row[0..8) <- g ; TB row <- h2 ; xb keeps h1
+L4D_HD void l4d_bw_flow_a(const DevModel& M, const BwSample& s, const float* flow_in, size_t stride,
+                          const float g[6], float* xb, int xs, float* ta_row, float* tb_row) {
+  float yv[L4D_H];
+#pragma unroll
+  for (int k = 0; k < L4D_FLOW_IN; ++k) xb[k * xs] = s.active ? flow_in[(size_t)k * stride] : 0.f;
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) yv[k] = 0.f;
+  l4d_layer64(yv, xb, xs, L4D_FLOW_IN, M.flo_w0t);
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) xb[k * xs] = fmaxf(yv[k], 0.f);            // h1
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) yv[k] = 0.f;
+  l4d_layer64(yv, xb, xs, L4D_H, M.flo_w1t);
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) tb_row[k] = s.active ? fmaxf(yv[k], 0.f) : 0.f;   // h2
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ta_row[k] = (s.active && k < 6) ? g[k] : 0.f;
+}
+// step b: dh2 = (W2^T g) * relu2 ; TB row <- dh2 ; TA row <- h1 (from xb) ; xb <- dh2
+L4D_HD void l4d_bw_flow_b(const DevModel& M, const BwSample& s, const float g[6], float* xb, int xs,
+                          float* ta_row, float* tb_row) {
+  float d[L4D_H];
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) { d[k] = 0.f; ta_row[k] = s.active ? xb[k * xs] : 0.f; }
+  if (s.active) {
+#pragma unroll
+    for (int o = 0; o < 6; ++o) l4d_axpy64(d, g[o], M.flo_w2 + (size_t)o * L4D_H);
+  }
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) {
+    d[k] = l4d_bit(s.mf2a, s.mf2b, k) ? d[k] : 0.f;
+    tb_row[k] = d[k];
+    xb[k * xs] = d[k];
+  }
+}
+// step c: dh1 = (W1^T dh2) * relu1 ; TB row <- dh1 ; TA row[0..16) <- flow_in ; then the grid scatter
+L4D_HD void l4d_bw_flow_c(const DevModel& M, const L4DFrame& F, const DevGrads& G, const BwSample& s,
+                          const float* flow_in, size_t stride, float* xb, int xs, float* ta_row, float* tb_row) {
+  float d[L4D_H];
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) d[k] = 0.f;
+  l4d_layer64(d, xb, xs, L4D_H, M.flo_w1);                 // native [o][k]
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) {
+    d[k] = l4d_bit(s.mf1a, s.mf1b, k) ? d[k] : 0.f;
+    tb_row[k] = d[k];
+  }
+#pragma unroll
+  for (int k = 0; k < L4D_FLOW_IN; ++k) ta_row[k] = s.active ? flow_in[(size_t)k * stride] : 0.f;
+  if (!s.active) return;
+  // d(flow_in)[i] = W0[:, i] . dh1 ; feature (l, 2i+c) of the grid gets basis[i] * d(flow_in)[2l+c]
+#pragma unroll 1
+  for (int l = 0; l < 8; ++l) {
+    const float d0 = l4d_dot64(d, M.flo_w0t + (size_t)(2 * l) * L4D_H);
+    const float d1 = l4d_dot64(d, M.flo_w0t + (size_t)(2 * l + 1) * L4D_H);
+    uint32_t idx[8]; float w[8];
+    l4d_corners3(M.gf, l, s.x, s.y, s.z, idx, w);
+    float* base = G.hf + (size_t)M.gf.offset[l] * 8;
+    const float* b = F.flow_basis;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float* p = base + (size_t)idx[c] * 8;
+      l4d_red4(p, w[c] * b[0] * d0, w[c] * b[0] * d1, w[c] * b[1] * d0, w[c] * b[1] * d1);
+      l4d_red4(p + 4, w[c] * b[2] * d0, w[c] * b[2] * d1, w[c] * b[3] * d0, w[c] * b[3] * d1);
+    }
+  }
+}

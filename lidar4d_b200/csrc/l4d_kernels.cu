@@ -1,0 +1,889 @@
+// l4d_kernels.cu - sm_100a kernels and the C-ABI of liblidar4d_b200.so
+// (include/lidar4d_b200.h).  Thread == sample; one CTA walks one ray tile by
+// tile and carries the transmittance; persistent grid over rays.
+//
+// Reference path replaced: model/renderer.py:44-140 (LiDAR_Renderer.run),
+// model/lidar4d.py:124-223 (flow/density/attribute) and the encoders under it.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "l4d_bwd.cuh"
+#include "l4d_core.cuh"
+#include "l4d_host.h"
+
+// =============================================================================
+// error plumbing
+// =============================================================================
+static thread_local char g_err[512] = "";
+int l4d_fail(int code, const char* fmt, const char* a, const char* b) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+#define L4D_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) return l4d_fail(L4D_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" int l4d_abi_version(void) { return L4D_ABI_VERSION; }
+extern "C" const char* l4d_last_error(void) { return g_err; }
+
+// =============================================================================
+// staging kernels (once per optimiser step; pure HBM streaming)
+// =============================================================================
+__global__ void k_cast_half(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i * 4 + 3 < n; i += stride) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+}
+// NCHW [8][H*W] -> channels-last [H*W][8]
+__global__ void k_plane_to_cl(const float* __restrict__ src, float* __restrict__ dst, int hw) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hw * 8) return;
+  int c = i & 7, px = i >> 3;
+  dst[i] = __ldg(src + (size_t)c * hw + px);
+}
+// channels-last grad -> += NCHW grad
+__global__ void k_plane_from_cl(const float* __restrict__ src, float* __restrict__ dst, int hw) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hw * 8) return;
+  int px = i % hw, c = i / hw;
+  dst[i] += src[(size_t)px * 8 + c];
+}
+// dst[c][r] = src[r][c] (src rows x cols); rows_valid/cols_valid select a sub-block, rest zero
+__global__ void k_transpose(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int dst_rows,
+                            int dst_cols, int valid_rows, int valid_cols) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dst_rows * dst_cols) return;
+  int r = i / dst_cols, c = i % dst_cols;       // dst[r][c] = src[c][r]
+  dst[i] = (r < valid_rows && c < valid_cols) ? __ldg(src + (size_t)c * src_ld + r) : 0.f;
+}
+__global__ void k_copy_block(const float* __restrict__ src, float* __restrict__ dst, int n_valid, int n_total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  dst[i] = i < n_valid ? __ldg(src + i) : 0.f;
+}
+// dst[r][c] += src[c][r]   (fold an in-major work gradient into a native-layout master gradient)
+__global__ void k_add_transposed(const float* __restrict__ src, int src_cols, float* __restrict__ dst, int dst_rows,
+                                 int dst_cols) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dst_rows * dst_cols) return;
+  int r = i / dst_cols, c = i % dst_cols;
+  dst[i] += src[(size_t)c * src_cols + r];
+}
+__global__ void k_add(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+static inline int nblk(size_t n, int t = 256) { return (int)((n + t - 1) / t); }
+
+extern "C" size_t l4d_staged_bytes(const L4DConfig* cfg) {
+  if (check_config(cfg) != L4D_OK) return 0;
+  return staged_layout(cfg).total;
+}
+
+extern "C" int l4d_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, void* staged, size_t staged_bytes,
+                                void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  if (!m || !staged) return l4d_fail(L4D_EINVAL, "null pointer");
+  StagedLayout L = staged_layout(cfg);
+  if (staged_bytes < L.total) return l4d_fail(L4D_ESIZE, "staged buffer too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* b = reinterpret_cast<char*>(staged);
+  auto H = [&](size_t off) { return reinterpret_cast<__half*>(b + off); };
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(b + off); };
+  {
+    size_t n = (size_t)cfg->hash_static.offset[cfg->hash_static.n_levels] * 4;
+    k_cast_half<<<2048, 256, 0, st>>>(m->hash_static, H(L.hs), n);
+  }
+  for (int p = 0; p < 3; ++p) {
+    size_t n = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels] * 4;
+    for (uint32_t s = 0; s < cfg->time_resolution; ++s) {
+      if (!m->hash_dynamic[p][s]) return l4d_fail(L4D_EINVAL, "null hash_dynamic slice");
+      k_cast_half<<<512, 256, 0, st>>>(m->hash_dynamic[p][s], H(L.hd[p]) + (size_t)s * n, n);
+    }
+  }
+  {
+    size_t n = (size_t)cfg->flow.offset[cfg->flow.n_levels] * 8;
+    k_cast_half<<<2048, 256, 0, st>>>(m->flow_grid, H(L.hf), n);
+  }
+  for (uint32_t s = 0; s < cfg->n_plane_scales; ++s)
+    for (int ci = 0; ci < 6; ++ci) {
+      int Hh, W;
+      plane_hw(cfg, s, ci, Hh, W);
+      k_plane_to_cl<<<nblk((size_t)Hh * W * 8), 256, 0, st>>>(m->planes[s][ci], F(L.planes[s][ci]), Hh * W);
+    }
+  // sigma net: params = [64][in_pad] | [16][64]
+  const int ip = (int)cfg->sigma_in_pad;
+  k_transpose<<<nblk((size_t)ip * 64), 256, 0, st>>>(m->sigma_net, ip, F(L.sig_w1t), ip, 64, ip, 64);
+  k_transpose<<<nblk(64 * 16), 256, 0, st>>>(m->sigma_net + 64 * ip, 64, F(L.sig_w2t), 64, 16, 64, 16);
+  k_copy_block<<<nblk(16 * 64), 256, 0, st>>>(m->sigma_net + 64 * ip, F(L.sig_w2), 16 * 64, 16 * 64);
+  // attribute nets: [64][96] | [64][64] | [16][64]; image channel 0 = raydrop, 1 = intensity (lidar4d.py:216)
+  const float* att[2] = {m->raydrop_net, m->intensity_net};
+  const int ap = (int)cfg->attr_in_pad;
+  for (int n = 0; n < 2; ++n) {
+    k_transpose<<<nblk((size_t)ap * 64), 256, 0, st>>>(att[n], ap, F(L.att_w1t[n]), ap, 64, ap, 64);
+    k_transpose<<<nblk(64 * 64), 256, 0, st>>>(att[n] + 64 * ap, 64, F(L.att_w2t[n]), 64, 64, 64, 64);
+    k_copy_block<<<nblk(64 * 64), 256, 0, st>>>(att[n] + 64 * ap, F(L.att_w2[n]), 64 * 64, 64 * 64);
+    k_copy_block<<<1, 64, 0, st>>>(att[n] + 64 * ap + 64 * 64, F(L.att_w3[n]), 64, 64);
+  }
+  // flow MLP: [64][16], [64][64], [6][64]
+  k_transpose<<<nblk(16 * 64), 256, 0, st>>>(m->flow_mlp[0], 16, F(L.flo_w0t), 16, 64, 16, 64);
+  k_transpose<<<nblk(64 * 64), 256, 0, st>>>(m->flow_mlp[1], 64, F(L.flo_w1t), 64, 64, 64, 64);
+  k_copy_block<<<nblk(64 * 64), 256, 0, st>>>(m->flow_mlp[1], F(L.flo_w1), 64 * 64, 64 * 64);
+  k_transpose<<<nblk(64 * 8), 256, 0, st>>>(m->flow_mlp[2], 64, F(L.flo_w2t), 64, 8, 64, 6);
+  k_copy_block<<<nblk(8 * 64), 256, 0, st>>>(m->flow_mlp[2], F(L.flo_w2), 6 * 64, 8 * 64);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+extern "C" size_t l4d_grad_work_bytes(const L4DConfig* cfg) {
+  if (check_config(cfg) != L4D_OK) return 0;
+  return grad_work_layout(cfg).total;
+}
+
+extern "C" int l4d_unstage_grads(const L4DConfig* cfg, const void* grad_work, size_t grad_work_bytes,
+                                 const L4DMasterGrads* g, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  if (!grad_work || !g) return l4d_fail(L4D_EINVAL, "null pointer");
+  GradWorkLayout L = grad_work_layout(cfg);
+  if (grad_work_bytes < L.total) return l4d_fail(L4D_ESIZE, "grad_work buffer too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const char* b = reinterpret_cast<const char*>(grad_work);
+  auto F = [&](size_t off) { return reinterpret_cast<const float*>(b + off); };
+  for (uint32_t s = 0; s < cfg->n_plane_scales; ++s)
+    for (int ci = 0; ci < 6; ++ci) {
+      int Hh, W;
+      plane_hw(cfg, s, ci, Hh, W);
+      if (g->planes[s][ci]) k_plane_from_cl<<<nblk((size_t)Hh * W * 8), 256, 0, st>>>(F(L.planes[s][ci]), g->planes[s][ci], Hh * W);
+    }
+  const int ip = (int)cfg->sigma_in_pad, ap = (int)cfg->attr_in_pad;
+  if (g->sigma_net) {
+    k_add_transposed<<<nblk((size_t)64 * ip), 256, 0, st>>>(F(L.sig_w1t), 64, g->sigma_net, 64, ip);
+    k_add<<<nblk(16 * 64), 256, 0, st>>>(F(L.sig_w2), g->sigma_net + 64 * ip, 16 * 64);
+  }
+  float* att[2] = {g->raydrop_net, g->intensity_net};
+  for (int n = 0; n < 2; ++n) {
+    if (!att[n]) continue;
+    k_add_transposed<<<nblk((size_t)64 * ap), 256, 0, st>>>(F(L.att_w1t[n]), 64, att[n], 64, ap);
+    k_add_transposed<<<nblk(64 * 64), 256, 0, st>>>(F(L.att_w2t[n]), 64, att[n] + 64 * ap, 64, 64);
+    k_add<<<1, 64, 0, st>>>(F(L.att_w3[n]), att[n] + 64 * ap + 64 * 64, 64);   // row 0 of the [16][64] output layer
+  }
+  if (g->flow_mlp[0]) k_add_transposed<<<nblk(64 * 16), 256, 0, st>>>(F(L.flo_w0t), 64, g->flow_mlp[0], 64, 16);
+  if (g->flow_mlp[1]) k_add_transposed<<<nblk(64 * 64), 256, 0, st>>>(F(L.flo_w1t), 64, g->flow_mlp[1], 64, 64);
+  if (g->flow_mlp[2]) k_add<<<nblk(6 * 64), 256, 0, st>>>(F(L.flo_w2), g->flow_mlp[2], 6 * 64);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+// =============================================================================
+// block-level primitives
+// =============================================================================
+template <int NT>
+__device__ __forceinline__ float block_excl_prod(float v, float* s_w, float& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc *= t;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  float ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) ex = 1.f;
+  __syncthreads();
+  float pre = 1.f, tot = 1.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) {
+    float t = s_w[w];
+    if (w < warp) pre *= t;
+    tot *= t;
+  }
+  total = tot;
+  __syncthreads();
+  return pre * ex;
+}
+
+// exclusive suffix sum: result_j = sum_{k>j} v_k within the block; total = sum of all
+template <int NT>
+__device__ __forceinline__ float block_excl_suffix_sum(float v, float* s_w, float& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_down_sync(0xffffffffu, inc, o);
+    if (lane + o < 32) inc += t;
+  }
+  if (lane == 0) s_w[warp] = inc;
+  float ex = __shfl_down_sync(0xffffffffu, inc, 1);
+  if (lane == 31) ex = 0.f;
+  __syncthreads();
+  float post = 0.f, tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) {
+    float t = s_w[w];
+    if (w > warp) post += t;
+    tot += t;
+  }
+  total = tot;
+  __syncthreads();
+  return post + ex;
+}
+
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* s_w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) s_w[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) t += s_w[w];
+  __syncthreads();
+  return t;
+}
+
+// dW[k][0..64) += sum_m TA[m][k] * TB[m][0..64) for k < K (K multiple of 8, <= 64); all NT threads.
+// Work items = 16-row blocks of k x m-ranges, one per warp; lanes own columns j and j+32.
+template <int NT>
+__device__ __forceinline__ void tile_outer_accum(const float* __restrict__ TA, const float* __restrict__ TB, int K,
+                                                 float* __restrict__ dW) {
+  constexpr int NW = NT / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nkb = (K + 15) / 16;
+  const int ms = nkb >= NW ? 1 : NW / nkb;
+  const int items = nkb * ms;
+  const int mlen = NT / ms;
+  for (int it = warp; it < items; it += NW) {
+    const int kb = it / ms, k0 = kb * 16;
+    const int m0 = (it % ms) * mlen;
+    float a0[16], a1[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+    for (int m = m0; m < m0 + mlen; ++m) {
+      const float4* ar = reinterpret_cast<const float4*>(TA + (size_t)m * L4D_TILE_LD + k0);
+      const float b0 = TB[(size_t)m * L4D_TILE_LD + lane];
+      const float b1 = TB[(size_t)m * L4D_TILE_LD + lane + 32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = ar[q];
+        a0[4 * q + 0] = fmaf(a.x, b0, a0[4 * q + 0]); a1[4 * q + 0] = fmaf(a.x, b1, a1[4 * q + 0]);
+        a0[4 * q + 1] = fmaf(a.y, b0, a0[4 * q + 1]); a1[4 * q + 1] = fmaf(a.y, b1, a1[4 * q + 1]);
+        a0[4 * q + 2] = fmaf(a.z, b0, a0[4 * q + 2]); a1[4 * q + 2] = fmaf(a.z, b1, a1[4 * q + 2]);
+        a0[4 * q + 3] = fmaf(a.w, b0, a0[4 * q + 3]); a1[4 * q + 3] = fmaf(a.w, b1, a1[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k0 + k < K) {
+        atomicAdd(dW + (size_t)(k0 + k) * 64 + lane, a0[k]);
+        atomicAdd(dW + (size_t)(k0 + k) * 64 + lane + 32, a1[k]);
+      }
+    }
+  }
+}
+
+// column sums of a tile: out[j] = sum_m T[m][j], j<64.  threads 0..63 return their column's sum
+template <int NT>
+__device__ __forceinline__ float tile_colsum(const float* __restrict__ T) {
+  float s = 0.f;
+  if (threadIdx.x < 64) {
+    for (int m = 0; m < NT; ++m) s += T[(size_t)m * L4D_TILE_LD + threadIdx.x];
+  }
+  return s;
+}
+
+// =============================================================================
+// forward render kernel
+// =============================================================================
+struct FwdArgs {
+  DevModel M;
+  L4DFrame F;
+  const float* rays_o;
+  const float* rays_d;
+  uint32_t n_rays, S, perturb;
+  uint64_t seed, ray_offset;
+  float *depth, *image, *wsum, *weights, *zvals;
+  SavedView sv;
+  uint32_t train;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_render_fwd(const __grid_constant__ FwdArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xbuf = smem;                 // [64][NT]
+  float* s_enc = xbuf + 64 * NT;      // [80]
+  float* s_cdir = s_enc + 80;         // [128]
+  float* s_w = s_cdir + 128;          // [32]
+  const DevModel& M = A.M;
+  const L4DFrame& F = A.F;
+  const int tid = threadIdx.x;
+  float* xb = xbuf + tid;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  const uint32_t S = A.S;
+
+  for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
+    const float ox = __ldg(A.rays_o + 3 * ray), oy = __ldg(A.rays_o + 3 * ray + 1), oz = __ldg(A.rays_o + 3 * ray + 2);
+    const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
+    __syncthreads();
+    for (int i = tid; i < L4D_ENC; i += NT) {
+      const int dim = i / 24, k = (i % 24) >> 1, ph = i & 1;
+      s_enc[i] = l4d_freq(dim == 0 ? dx : (dim == 1 ? dy : dz), k, ph);
+    }
+    __syncthreads();
+    for (int i = tid; i < 128; i += NT) s_cdir[i] = l4d_attr_cdir(M, i >> 6, i & 63, s_enc);
+    __syncthreads();
+
+    float carry = 1.f, pd = 0.f, p0 = 0.f, p1 = 0.f, pw = 0.f;
+    const uint64_t rg = A.ray_offset + ray;
+    for (uint32_t j0 = 0; j0 < S; j0 += NT) {
+      const uint32_t j = j0 + tid;
+      const bool valid = j < S;
+      const size_t p = (size_t)ray * S + j;
+      float zj = 0.f, alpha = 0.f, sigma = 0.f, geo[L4D_GEO];
+      if (valid) {
+        zj = l4d_z(rs, rg, j);
+        const float delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
+        const float x = l4d_x01(ox, dx, zj, M.bound), y = l4d_x01(oy, dy, zj, M.bound), z = l4d_x01(oz, dz, zj, M.bound);
+        FeatSink sink;
+        sink.feat = A.train ? A.sv.feat : nullptr;
+        sink.P = A.sv.P;
+        sink.p = p;
+        sink.dense = nullptr;
+        float h0, fl[6];
+        l4d_density_sample(M, F, x, y, z, xb, NT, sink, A.train ? A.sv.flow_in + p : nullptr, A.sv.P, sigma, h0, geo, fl);
+        alpha = l4d_alpha(M, delta, sigma);
+      }
+      const float v = valid ? (1.0f - alpha) + 1e-15f : 1.f;
+      float total;
+      const float T = carry * block_excl_prod<NT>(v, s_w, total);
+      carry *= total;
+      const float w = alpha * T;
+      float a0 = 0.f, a1 = 0.f;
+      if (valid && w > 1e-4f) {
+        a0 = l4d_attr_net(M, 0, s_cdir, geo, xb, NT);
+        a1 = l4d_attr_net(M, 1, s_cdir, geo, xb, NT);
+      }
+      pd = fmaf(w, zj, pd); p0 = fmaf(w, a0, p0); p1 = fmaf(w, a1, p1); pw += w;
+      if (valid) {
+        if (A.train) { A.sv.sigma[p] = sigma; A.sv.attr[p] = a0; A.sv.attr[A.sv.P + p] = a1; }
+        if (A.weights) A.weights[p] = w;
+        if (A.zvals) A.zvals[p] = zj;
+      }
+    }
+    pd = block_sum<NT>(pd, s_w); p0 = block_sum<NT>(p0, s_w); p1 = block_sum<NT>(p1, s_w); pw = block_sum<NT>(pw, s_w);
+    if (tid == 0) {
+      A.depth[ray] = pd; A.image[2 * ray] = p0; A.image[2 * ray + 1] = p1; A.wsum[ray] = pw;
+    }
+  }
+}
+
+// =============================================================================
+// backward render kernel
+// =============================================================================
+#define L4D_MAX_TILES 64
+struct BwdArgs {
+  DevModel M;
+  L4DFrame F;
+  DevGrads G;
+  const float* rays_o;
+  const float* rays_d;
+  uint32_t n_rays, S, perturb;
+  uint64_t seed, ray_offset;
+  const float *g_depth, *g_image, *g_wsum, *g_weights;
+  SavedView sv;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_render_bwd(const __grid_constant__ BwdArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xbuf = smem;                             // [64][NT]
+  float* TA = xbuf + 64 * NT;                     // [NT][LD]
+  float* TB = TA + NT * L4D_TILE_LD;              // [NT][LD]
+  float* s_enc = TB + NT * L4D_TILE_LD;           // [80]
+  float* s_cdir = s_enc + 80;                     // [128]
+  float* s_csum = s_cdir + 128;                   // [128]
+  float* s_w = s_csum + 128;                      // [32]
+  float* s_tstart = s_w + 32;                     // [L4D_MAX_TILES]
+  const DevModel& M = A.M;
+  const L4DFrame& F = A.F;
+  const DevGrads& G = A.G;
+  const int tid = threadIdx.x;
+  float* xb = xbuf + tid;
+  float* ta_row = TA + (size_t)tid * L4D_TILE_LD;
+  float* tb_row = TB + (size_t)tid * L4D_TILE_LD;
+  float* hid = A.sv.hidden + (size_t)blockIdx.x * 64 * NT + tid;   // per-CTA scratch column, stride NT
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  const uint32_t S = A.S;
+  const int n_tiles = (int)((S + NT - 1) / NT);
+  const float kk = M.active_sensor ? 2.0f : 1.0f;
+  const int n_chunks = (int)(M.sigma_in_pad + 63) / 64;
+
+  for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
+    const float ox = __ldg(A.rays_o + 3 * ray), oy = __ldg(A.rays_o + 3 * ray + 1), oz = __ldg(A.rays_o + 3 * ray + 2);
+    const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
+    const float gd = __ldg(A.g_depth + ray), gi0 = __ldg(A.g_image + 2 * ray), gi1 = __ldg(A.g_image + 2 * ray + 1);
+    const float gws = A.g_wsum ? __ldg(A.g_wsum + ray) : 0.f;
+    const uint64_t rg = A.ray_offset + ray;
+    __syncthreads();
+    for (int i = tid; i < L4D_ENC; i += NT) {
+      const int dim = i / 24, k = (i % 24) >> 1, ph = i & 1;
+      s_enc[i] = l4d_freq(dim == 0 ? dx : (dim == 1 ? dy : dz), k, ph);
+    }
+    for (int i = tid; i < 128; i += NT) s_csum[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < 128; i += NT) s_cdir[i] = l4d_attr_cdir(M, i >> 6, i & 63, s_enc);
+    __syncthreads();
+
+    // ---- pass 1: transmittance at the start of every tile ----
+    {
+      float carry = 1.f;
+      for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t j = (uint32_t)t * NT + tid;
+        const bool valid = j < S;
+        float v = 1.f;
+        if (valid) {
+          const float zj = l4d_z(rs, rg, j);
+          const float delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
+          const float alpha = l4d_alpha(M, delta, A.sv.sigma[(size_t)ray * S + j]);
+          v = (1.0f - alpha) + 1e-15f;
+        }
+        if (tid == 0) s_tstart[t] = carry;
+        float total;
+        block_excl_prod<NT>(v, s_w, total);
+        carry *= total;
+      }
+    }
+    __syncthreads();
+
+    // ---- pass 2: tiles in reverse, carrying the suffix sum of dL/dw * w ----
+    float suffix = 0.f;
+    for (int t = n_tiles - 1; t >= 0; --t) {
+      const uint32_t j = (uint32_t)t * NT + tid;
+      const size_t p = (size_t)ray * S + j;
+      BwSample s;
+      s.active = j < S;
+      s.masked = false;
+      s.dsigma = 0.f; s.da[0] = 0.f; s.da[1] = 0.f;
+      s.x = s.y = s.z = 0.f;
+      float v = 1.f, q = 0.f, alpha = 0.f, gw = 0.f, delta = 0.f;
+      if (s.active) {
+        const float zj = l4d_z(rs, rg, j);
+        delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
+        s.x = l4d_x01(ox, dx, zj, M.bound); s.y = l4d_x01(oy, dy, zj, M.bound); s.z = l4d_x01(oz, dz, zj, M.bound);
+        alpha = l4d_alpha(M, delta, A.sv.sigma[p]);
+        v = (1.0f - alpha) + 1e-15f;
+        gw = gd * zj + gi0 * A.sv.attr[p] + gi1 * A.sv.attr[A.sv.P + p] + gws;
+        if (A.g_weights) gw += __ldg(A.g_weights + p);
+      }
+      float total;
+      const float T = s_tstart[t] * block_excl_prod<NT>(v, s_w, total);
+      const float w = alpha * T;
+      q = gw * w;
+      float qtot;
+      const float suf = suffix + block_excl_suffix_sum<NT>(q, s_w, qtot);
+      suffix += qtot;
+      if (s.active) {
+        const float dalpha = gw * T - suf / v;
+        s.dsigma = dalpha * (kk * delta * M.density_scale) * (1.0f - alpha);
+        s.masked = w > 1e-4f;
+        if (s.masked) { s.da[0] = w * gi0; s.da[1] = w * gi1; }
+      }
+
+      // B0 / B1: recompute flow + sigma MLP forward
+      l4d_bw_flow_fwd(M, s, A.sv.flow_in + p, A.sv.P, xb, NT);
+      l4d_bw_sigma_fwd(M, s, A.sv.feat + p, A.sv.P, xb, NT, hid, NT);
+
+      // B2: attribute heads
+#pragma unroll 1
+      for (int net = 0; net < 2; ++net) {
+        uint32_t m1a, m1b;
+        l4d_bw_attr_a(M, net, s, s_cdir, xb, NT, ta_row, tb_row, m1a, m1b);
+        __syncthreads();
+        {
+          const float cs = tile_colsum<NT>(TB);
+          if (tid < 64) atomicAdd(G.att_w3[net] + tid, cs);
+        }
+        __syncthreads();
+        l4d_bw_attr_b(xb, NT, tb_row);
+        __syncthreads();
+        tile_outer_accum<NT>(TA, TB, 64, G.att_w2t[net]);
+        __syncthreads();
+        l4d_bw_attr_c(M, net, s, xb, NT, ta_row, tb_row, m1a, m1b);
+        __syncthreads();
+        tile_outer_accum<NT>(TA, TB, 16, G.att_w1t[net] + (size_t)L4D_ENC * 64);
+        {
+          const float cs = tile_colsum<NT>(TB);
+          if (tid < 64) s_csum[net * 64 + tid] += cs;
+        }
+        __syncthreads();
+      }
+
+      // B3: sigma MLP backprop
+      l4d_bw_sigma_a(M, s, hid, NT, xb, NT, ta_row, tb_row);
+      __syncthreads();
+      tile_outer_accum<NT>(TA, TB, 16, G.sig_w2);
+      __syncthreads();
+      l4d_bw_sigma_b(M, s, xb, NT, tb_row);
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        l4d_bw_sigma_c(M, s, A.sv.feat + p, A.sv.P, c, ta_row);
+        __syncthreads();
+        const int rows = min(64, (int)M.sigma_in_pad - c * 64);
+        tile_outer_accum<NT>(TA, TB, rows, G.sig_w1t + (size_t)c * 64 * 64);
+        __syncthreads();
+      }
+
+      // B4: encoders
+      l4d_bw_scatter(M, F, G, s);
+
+      // B5: flow MLP backprop + flow grid
+      l4d_bw_flow_a(M, s, A.sv.flow_in + p, A.sv.P, s.dflow, xb, NT, ta_row, tb_row);
+      __syncthreads();
+      tile_outer_accum<NT>(TA, TB, 8, G.flo_w2);
+      __syncthreads();
+      l4d_bw_flow_b(M, s, s.dflow, xb, NT, ta_row, tb_row);
+      __syncthreads();
+      tile_outer_accum<NT>(TA, TB, 64, G.flo_w1t);
+      __syncthreads();
+      l4d_bw_flow_c(M, F, G, s, A.sv.flow_in + p, A.sv.P, xb, NT, ta_row, tb_row);
+      __syncthreads();
+      tile_outer_accum<NT>(TA, TB, 16, G.flo_w0t);
+      __syncthreads();
+    }
+
+    // direction / ones rows of the first attribute layer: dW1t[k][j] += enc[k] * sum_samples dh1[j]
+    for (int i = tid; i < 2 * (L4D_ENC + 9) * 64; i += NT) {
+      const int net = i / ((L4D_ENC + 9) * 64);
+      const int r = (i / 64) % (L4D_ENC + 9), jx = i & 63;
+      const float cs = s_csum[net * 64 + jx];
+      if (r < L4D_ENC) atomicAdd(G.att_w1t[net] + (size_t)r * 64 + jx, s_enc[r] * cs);
+      else atomicAdd(G.att_w1t[net] + (size_t)(M.attr_in_dim + (r - L4D_ENC)) * 64 + jx, cs);
+    }
+  }
+}
+
+// =============================================================================
+// flow-only kernels (LiDAR4D.flow, lidar4d.py:124-137)
+// =============================================================================
+struct FlowArgs {
+  DevModel M;
+  L4DFrame F;
+  DevGrads G;
+  const float* x;
+  uint32_t n;
+  float* flow;
+  float* saved;         // [16][n] or null
+  const float* g_flow;  // [n][6]
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_flow_fwd(const __grid_constant__ FlowArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xb = smem + threadIdx.x;
+  const DevModel& M = A.M;
+  for (uint32_t base = blockIdx.x * NT; base < A.n; base += gridDim.x * NT) {
+    const uint32_t i = base + threadIdx.x;
+    if (i < A.n) {
+      const float b2 = L4D_MUL(2.0f, M.bound);
+      const float x = L4D_DIV(L4D_ADD(__ldg(A.x + 3 * i), M.bound), b2);
+      const float y = L4D_DIV(L4D_ADD(__ldg(A.x + 3 * i + 1), M.bound), b2);
+      const float z = L4D_DIV(L4D_ADD(__ldg(A.x + 3 * i + 2), M.bound), b2);
+      l4d_flow_inputs(M, A.F.flow_basis, x, y, z, xb, NT, A.saved ? A.saved + i : nullptr, A.n);
+      float fl[8];
+      uint32_t a, b, c, d;
+      l4d_flow_mlp(M, xb, NT, fl, a, b, c, d);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) A.flow[(size_t)i * 6 + k] = fl[k];
+    }
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_flow_bwd(const __grid_constant__ FlowArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xbuf = smem;
+  float* TA = xbuf + 64 * NT;
+  float* TB = TA + NT * L4D_TILE_LD;
+  float* xb = xbuf + threadIdx.x;
+  float* ta_row = TA + (size_t)threadIdx.x * L4D_TILE_LD;
+  float* tb_row = TB + (size_t)threadIdx.x * L4D_TILE_LD;
+  const DevModel& M = A.M;
+  for (uint32_t base = blockIdx.x * NT; base < A.n; base += gridDim.x * NT) {
+    const uint32_t i = base + threadIdx.x;
+    BwSample s;
+    s.active = i < A.n;
+    s.masked = false;
+    s.x = s.y = s.z = 0.f;
+    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const size_t ii = s.active ? i : 0;
+    if (s.active) {
+      const float b2 = L4D_MUL(2.0f, M.bound);
+      s.x = L4D_DIV(L4D_ADD(__ldg(A.x + 3 * i), M.bound), b2);
+      s.y = L4D_DIV(L4D_ADD(__ldg(A.x + 3 * i + 1), M.bound), b2);
+      s.z = L4D_DIV(L4D_ADD(__ldg(A.x + 3 * i + 2), M.bound), b2);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) g[k] = __ldg(A.g_flow + (size_t)i * 6 + k);
+    }
+    __syncthreads();
+    l4d_bw_flow_fwd(M, s, A.saved + ii, A.n, xb, NT);
+    l4d_bw_flow_a(M, s, A.saved + ii, A.n, g, xb, NT, ta_row, tb_row);
+    __syncthreads();
+    tile_outer_accum<NT>(TA, TB, 8, A.G.flo_w2);
+    __syncthreads();
+    l4d_bw_flow_b(M, s, g, xb, NT, ta_row, tb_row);
+    __syncthreads();
+    tile_outer_accum<NT>(TA, TB, 64, A.G.flo_w1t);
+    __syncthreads();
+    l4d_bw_flow_c(M, A.F, A.G, s, A.saved + ii, A.n, xb, NT, ta_row, tb_row);
+    __syncthreads();
+    tile_outer_accum<NT>(TA, TB, 16, A.G.flo_w0t);
+  }
+}
+
+// =============================================================================
+// debug kernels
+// =============================================================================
+__global__ void k_hash_indices(DevGrid g, int D, int level, const float* x, uint32_t n, uint32_t* idx, float* w) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (D == 3) {
+    uint32_t id[8]; float ww[8];
+    l4d_corners3(g, level, x[3 * i], x[3 * i + 1], x[3 * i + 2], id, ww);
+    for (int c = 0; c < 8; ++c) { idx[8 * i + c] = id[c]; w[8 * i + c] = ww[c]; }
+  } else {
+    uint32_t id[4]; float ww[4];
+    l4d_corners2(g, level, x[2 * i], x[2 * i + 1], id, ww);
+    for (int c = 0; c < 4; ++c) { idx[4 * i + c] = id[c]; w[4 * i + c] = ww[c]; }
+  }
+}
+
+struct DensityArgs {
+  DevModel M;
+  L4DFrame F;
+  const float* x;
+  uint32_t n;
+  float *sigma, *geo, *features, *flow;
+};
+template <int NT>
+__global__ void __launch_bounds__(NT) k_density(const __grid_constant__ DensityArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xb = smem + threadIdx.x;
+  const DevModel& M = A.M;
+  const uint32_t i = blockIdx.x * NT + threadIdx.x;
+  if (i >= A.n) return;
+  const float b2 = L4D_MUL(2.0f, M.bound);
+  const float x = L4D_DIV(L4D_ADD(A.x[3 * i], M.bound), b2);
+  const float y = L4D_DIV(L4D_ADD(A.x[3 * i + 1], M.bound), b2);
+  const float z = L4D_DIV(L4D_ADD(A.x[3 * i + 2], M.bound), b2);
+  FeatSink sink;
+  sink.feat = nullptr; sink.P = 0; sink.p = 0;
+  sink.dense = A.features ? A.features + (size_t)i * M.sigma_in_dim : nullptr;
+  float sigma, h0, geo[L4D_GEO], fl[6];
+  l4d_density_sample(M, A.F, x, y, z, xb, NT, sink, nullptr, 0, sigma, h0, geo, fl);
+  A.sigma[i] = sigma;
+  for (int k = 0; k < L4D_GEO; ++k) A.geo[(size_t)i * L4D_GEO + k] = geo[k];
+  if (A.flow) for (int k = 0; k < 6; ++k) A.flow[(size_t)i * 6 + k] = fl[k];
+}
+
+// =============================================================================
+// C-ABI launchers
+// =============================================================================
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+extern "C" size_t l4d_saved_bytes(const L4DConfig* cfg, uint32_t n_rays, uint32_t n_steps) {
+  if (check_config(cfg) != L4D_OK) return 0;
+  return saved_layout(cfg, n_rays, n_steps).total;
+}
+
+static int check_rays(const L4DRays* r) {
+  if (!r || !r->rays_o || !r->rays_d) return l4d_fail(L4D_EINVAL, "null rays");
+  if (r->n_steps < 1 || r->n_steps > L4D_MAX_TILES * L4D_NT) return l4d_fail(L4D_EINVAL, "n_steps out of range [1, 8192]");
+  return L4D_OK;
+}
+
+template <typename K>
+static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid) {
+  int per_sm = 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
+  if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
+  if (per_sm < 1) per_sm = 1;
+  long g = (long)per_sm * sm_count();
+  if ((long)work < g) g = work;
+  if (g < 1) g = 1;
+  grid = (int)g;
+  return L4D_OK;
+}
+
+extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
+                                  float* depth, float* image, float* wsum, float* weights, float* zvals, void* saved,
+                                  size_t saved_bytes, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  rc = check_rays(rays);
+  if (rc != L4D_OK) return rc;
+  if (!staged || !frame || !depth || !image || !wsum) return l4d_fail(L4D_EINVAL, "null pointer");
+  if (rays->n_rays == 0) return L4D_OK;
+  FwdArgs A;
+  memset(&A, 0, sizeof(A));
+  build_model(cfg, staged, A.M);
+  A.F = *frame;
+  A.rays_o = rays->rays_o; A.rays_d = rays->rays_d;
+  A.n_rays = rays->n_rays; A.S = rays->n_steps; A.perturb = rays->perturb;
+  A.seed = rays->seed; A.ray_offset = rays->ray_offset;
+  A.depth = depth; A.image = image; A.wsum = wsum; A.weights = weights; A.zvals = zvals;
+  A.train = saved ? 1u : 0u;
+  if (saved) {
+    if (saved_bytes < saved_layout(cfg, rays->n_rays, rays->n_steps).total) return l4d_fail(L4D_ESIZE, "saved buffer too small");
+    A.sv = saved_view(cfg, saved, rays->n_rays, rays->n_steps);
+  }
+  const size_t smem = (64 * L4D_NT + 80 + 128 + 32) * sizeof(float);
+  int grid;
+  rc = grid_for(k_render_fwd<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
+  if (rc != L4D_OK) return rc;
+  k_render_fwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
+                                   const void* saved, size_t saved_bytes, const float* g_depth, const float* g_image,
+                                   const float* g_wsum, const float* g_weights, const L4DMasterGrads* grads,
+                                   void* grad_work, size_t grad_work_bytes, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  rc = check_rays(rays);
+  if (rc != L4D_OK) return rc;
+  if (!staged || !frame || !saved || !g_depth || !g_image || !grads || !grad_work) return l4d_fail(L4D_EINVAL, "null pointer");
+  if (saved_bytes < saved_layout(cfg, rays->n_rays, rays->n_steps).total) return l4d_fail(L4D_ESIZE, "saved buffer too small");
+  if (grad_work_bytes < grad_work_layout(cfg).total) return l4d_fail(L4D_ESIZE, "grad_work buffer too small");
+  if (!grads->hash_static || !grads->flow_grid) return l4d_fail(L4D_EINVAL, "null hash gradient buffer");
+  for (int p = 0; p < 3; ++p)
+    for (uint32_t s = 0; s < cfg->time_resolution; ++s)
+      if (!grads->hash_dynamic[p][s]) return l4d_fail(L4D_EINVAL, "null hash_dynamic gradient buffer");
+  if (rays->n_rays == 0) return L4D_OK;
+  BwdArgs A;
+  memset(&A, 0, sizeof(A));
+  build_model(cfg, staged, A.M);
+  build_grads(cfg, grads, grad_work, A.G);
+  A.F = *frame;
+  A.rays_o = rays->rays_o; A.rays_d = rays->rays_d;
+  A.n_rays = rays->n_rays; A.S = rays->n_steps; A.perturb = rays->perturb;
+  A.seed = rays->seed; A.ray_offset = rays->ray_offset;
+  A.g_depth = g_depth; A.g_image = g_image; A.g_wsum = g_wsum; A.g_weights = g_weights;
+  A.sv = saved_view(cfg, const_cast<void*>(saved), rays->n_rays, rays->n_steps);
+  const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD + 80 + 128 + 128 + 32 + L4D_MAX_TILES) * sizeof(float);
+  int grid;
+  rc = grid_for(k_render_bwd<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
+  if (rc != L4D_OK) return rc;
+  if (grid > L4D_BWD_SCRATCH_CTAS) grid = L4D_BWD_SCRATCH_CTAS;
+  k_render_bwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+extern "C" int l4d_flow_forward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const float* x,
+                                uint32_t n, float* flow, float* flow_saved, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  if (!staged || !frame || !x || !flow) return l4d_fail(L4D_EINVAL, "null pointer");
+  if (n == 0) return L4D_OK;
+  FlowArgs A;
+  memset(&A, 0, sizeof(A));
+  build_model(cfg, staged, A.M);
+  A.F = *frame; A.x = x; A.n = n; A.flow = flow; A.saved = flow_saved;
+  const size_t smem = 64 * L4D_NT * sizeof(float);
+  int grid;
+  rc = grid_for(k_flow_fwd<L4D_NT>, L4D_NT, smem, (n + L4D_NT - 1) / L4D_NT, grid);
+  if (rc != L4D_OK) return rc;
+  k_flow_fwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+extern "C" int l4d_flow_backward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const float* x,
+                                 uint32_t n, const float* flow_saved, const float* g_flow, const L4DMasterGrads* grads,
+                                 void* grad_work, size_t grad_work_bytes, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  if (!staged || !frame || !x || !flow_saved || !g_flow || !grads || !grad_work) return l4d_fail(L4D_EINVAL, "null pointer");
+  if (grad_work_bytes < grad_work_layout(cfg).total) return l4d_fail(L4D_ESIZE, "grad_work buffer too small");
+  if (!grads->flow_grid) return l4d_fail(L4D_EINVAL, "null flow_grid gradient buffer");
+  if (n == 0) return L4D_OK;
+  FlowArgs A;
+  memset(&A, 0, sizeof(A));
+  build_model(cfg, staged, A.M);
+  {
+    // only the flow sinks are touched; hash_static/dynamic may be null here
+    GradWorkLayout L = grad_work_layout(cfg);
+    char* b = reinterpret_cast<char*>(grad_work);
+    A.G.hf = grads->flow_grid;
+    A.G.flo_w0t = reinterpret_cast<float*>(b + L.flo_w0t);
+    A.G.flo_w1t = reinterpret_cast<float*>(b + L.flo_w1t);
+    A.G.flo_w2 = reinterpret_cast<float*>(b + L.flo_w2);
+  }
+  A.F = *frame; A.x = x; A.n = n; A.saved = const_cast<float*>(flow_saved); A.g_flow = g_flow;
+  const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD) * sizeof(float);
+  int grid;
+  rc = grid_for(k_flow_bwd<L4D_NT>, L4D_NT, smem, (n + L4D_NT - 1) / L4D_NT, grid);
+  if (rc != L4D_OK) return rc;
+  k_flow_bwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+extern "C" int l4d_hash_indices(const L4DConfig* cfg, uint32_t grid_id, uint32_t level, const float* x, uint32_t n,
+                                uint32_t* idx, float* w, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  if (grid_id > 4 || !x || !idx || !w) return l4d_fail(L4D_EINVAL, "bad argument");
+  const L4DGrid& g = grid_id == 0 ? cfg->hash_static : (grid_id == 4 ? cfg->flow : cfg->hash_dynamic[grid_id - 1]);
+  if (level >= g.n_levels) return l4d_fail(L4D_EINVAL, "level out of range");
+  if (n == 0) return L4D_OK;
+  DevGrid d;
+  fill_grid(d, g);
+  k_hash_indices<<<nblk(n), 256, 0, (cudaStream_t)stream>>>(d, (int)g.n_dims, (int)level, x, n, idx, w);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+extern "C" int l4d_density_forward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const float* x,
+                                   uint32_t n, float* sigma, float* geo, float* features, float* flow, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  if (!staged || !frame || !x || !sigma || !geo) return l4d_fail(L4D_EINVAL, "null pointer");
+  if (n == 0) return L4D_OK;
+  DensityArgs A;
+  memset(&A, 0, sizeof(A));
+  build_model(cfg, staged, A.M);
+  A.F = *frame; A.x = x; A.n = n; A.sigma = sigma; A.geo = geo; A.features = features; A.flow = flow;
+  const size_t smem = 64 * L4D_NT * sizeof(float);
+  L4D_CUDA(cudaFuncSetAttribute(k_density<L4D_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_density<L4D_NT><<<nblk(n, L4D_NT), L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}

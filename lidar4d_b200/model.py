@@ -1,0 +1,495 @@
+"""Drop-in `LiDAR4D` / `LiDAR_Renderer` nn.Modules backed by liblidar4d_b200.so.
+
+API mirrored from the reference (paths relative to the reference checkout):
+  LiDAR4D.__init__ kwargs           model/lidar4d.py:23-45, main_lidar4d.py:155-179
+  render(rays_o, rays_d, time, staged, max_ray_batch, **kw) -> dict   model/renderer.py:142-186
+  run(rays_o, rays_d, time, num_steps, perturb, **kw) -> dict         model/renderer.py:44-140
+  flow(x, t) -> {"forward","backward"}                                model/lidar4d.py:124-137
+  density(x, t) -> {"sigma","geo_feat"}                               model/lidar4d.py:139-188
+  get_params(lr)                                                      model/lidar4d.py:226-237
+  state_dict keys / shapes                                            SURVEY.md 8(b)
+
+There is no PyTorch/CPU implementation of the math in this file: every call
+lands in the CUDA library through ctypes and raises if that is impossible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _capi
+from .geometry import FieldConfig, make_frame
+
+
+# =============================================================================
+# parameter containers with the reference's module / parameter names
+# =============================================================================
+class _TcnnParams(nn.Module):
+    """Stands where a tcnn.Encoding / tcnn.Network stood: a flat fp32 `params`
+    vector and `n_output_dims` (hash_field.py:137-139, lidar4d.py:84,96,108)."""
+
+    def __init__(self, n_params: int, n_output_dims: int, init: str, **kw):
+        super().__init__()
+        self.n_output_dims = n_output_dims
+        p = torch.empty(n_params)
+        if init == "hash":
+            p.uniform_(-1e-4, 1e-4)                      # tcnn grid init [tcnn-ext]
+        elif init == "mlp":
+            o = 0
+            dims = kw["dims"]
+            for i in range(len(dims) - 1):               # xavier-uniform per [out,in] matrix [tcnn-ext]
+                n = dims[i] * dims[i + 1]
+                s = math.sqrt(6.0 / (dims[i] + dims[i + 1]))
+                p[o:o + n].uniform_(-s, s)
+                o += n
+        elif init == "empty":
+            pass
+        self.params = nn.Parameter(p)
+
+    def forward(self, *a, **k):
+        raise RuntimeError("encoders/MLPs are fused into the render kernel; call LiDAR4D.render/run/flow/density")
+
+
+class _HashGridT(nn.Module):
+    def __init__(self, n_params, time_resolution, n_output_dims):
+        super().__init__()
+        self.hash_t = nn.ModuleList([_TcnnParams(n_params, n_output_dims * 4, "hash") for _ in range(time_resolution)])
+        self.n_output_dims = n_output_dims
+
+
+class _HashGrid4D(nn.Module):
+    def __init__(self, cfg: FieldConfig):
+        super().__init__()
+        gs = cfg.static_grid()
+        self.hash_static = _TcnnParams(gs.n_params, gs.n_output_dims, "hash")
+        self.hash_dynamic = nn.ModuleList([
+            _HashGridT(cfg.dynamic_grid(p).n_params, cfg.time_resolution, cfg.hash_dynamic_dim // 3) for p in range(3)])
+        self.n_output_dims = cfg.hash_static_dim + cfg.hash_dynamic_dim
+
+
+class _Planes4D(nn.Module):
+    """planes_field.py:144-190: ModuleList over scales of ParameterList over the 6 planes."""
+
+    def __init__(self, cfg: FieldConfig):
+        super().__init__()
+        self.planes = nn.ModuleList()
+        combs = list(itertools.combinations(range(4), 2))
+        for mult in cfg.plane_scales:
+            reso = [cfg.min_resolution * mult] * 3 + [cfg.time_resolution]
+            pl = nn.ParameterList()
+            for comb in combs:
+                t = torch.empty([1, cfg.n_features_per_level_plane] + [reso[cc] for cc in comb[::-1]])
+                if 3 in comb:
+                    nn.init.ones_(t)
+                else:
+                    nn.init.uniform_(t, a=0.1, b=0.5)
+                pl.append(nn.Parameter(t))
+            self.planes.append(pl)
+        self.n_output_dims = 2 * cfg.plane_dim
+
+
+class _FlowField(nn.Module):
+    def __init__(self, cfg: FieldConfig):
+        super().__init__()
+        gf = cfg.flow_grid()
+        self.grid_enc = _TcnnParams(gf.n_params, gf.n_output_dims, "hash")
+        h = cfg.hidden_dim_flow
+        self.mlp = nn.Sequential(nn.Linear(gf.n_output_dims // 4, h, bias=False), nn.ReLU(),
+                                 nn.Linear(h, h, bias=False), nn.ReLU(), nn.Linear(h, 6, bias=False))
+        torch.nn.init.normal_(self.mlp[-1].weight.data, 0, 0.001)     # flow_field.py:100
+
+
+# =============================================================================
+# engine: staging, pointer tables, launches
+# =============================================================================
+class _Engine:
+    def __init__(self, owner: "LiDAR4D"):
+        self.owner = owner
+        self.cfg = owner.cfg
+        self.ccfg = _capi.make_config(self.cfg)
+        self.names = _capi.param_names(self.cfg)
+        self.lib = None
+        self.staged = None
+        self._stamp = None
+        self.n_launches = 0        # kernels of this library launched so far (bench "gpu_launches")
+
+    def _lib(self):
+        if self.lib is None:
+            self.lib = _capi.load_library()
+        return self.lib
+
+    def tensors(self) -> Dict[str, torch.Tensor]:
+        sd = dict(self.owner.named_parameters())
+        return {n: sd[n] for n in self.names}
+
+    def device(self) -> torch.device:
+        return self.owner.aabb.device
+
+    def _require_cuda(self, *ts):
+        dev = self.device()
+        if dev.type != "cuda":
+            raise RuntimeError("lidar4d_b200 runs on CUDA (sm_100a) only; move the model with .cuda() "
+                               "(there is no CPU fallback)")
+        for t in ts:
+            if t is not None and t.device != dev:
+                raise RuntimeError(f"tensor on {t.device}, model on {dev}")
+
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device()).cuda_stream
+
+    def ensure_staged(self):
+        """Refresh the fp16 / channels-last / transposed working set when any
+        master parameter changed (optimizer.step bumps tensor._version)."""
+        lib = self._lib()
+        ts = self.tensors()
+        stamp = tuple((t.data_ptr(), t._version) for t in ts.values())
+        if self.staged is not None and stamp == self._stamp and self.staged.device == self.device():
+            return
+        for n, t in ts.items():
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError(f"parameter {n} must be contiguous fp32")
+        nbytes = lib.l4d_staged_bytes(C.byref(self.ccfg))
+        if nbytes == 0:
+            raise RuntimeError("unsupported configuration: " + lib.l4d_last_error().decode())
+        if self.staged is None or self.staged.device != self.device():
+            self.staged = torch.empty(nbytes, dtype=torch.uint8, device=self.device())
+        tab = _capi.L4DMasterParams()
+        _capi.fill_pointer_table(tab, self.cfg, lambda n: ts[n].data_ptr())
+        with torch.cuda.device(self.device()):
+            rc = lib.l4d_stage_params(C.byref(self.ccfg), C.byref(tab), self.staged.data_ptr(), nbytes, self.stream())
+        _capi.check(lib, rc, "l4d_stage_params")
+        self.n_launches += 2 + 3 * self.cfg.time_resolution + 6 * self.cfg.n_levels_plane + 16
+        self._stamp = stamp
+
+    # ---- gradient arena -------------------------------------------------------
+    def new_grad_arena(self):
+        ts = self.tensors()
+        sizes = [ts[n].numel() for n in self.names]
+        offs = np.concatenate([[0], np.cumsum([(s + 63) // 64 * 64 for s in sizes])])
+        flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=self.device())
+        views = {n: flat[int(offs[i]):int(offs[i]) + sizes[i]].view_as(ts[n]) for i, n in enumerate(self.names)}
+        return flat, views
+
+    def grad_table(self, views):
+        tab = _capi.L4DMasterGrads()
+        _capi.fill_pointer_table(tab, self.cfg, lambda n: views[n].data_ptr())
+        return tab
+
+    def frame(self, time) -> _capi.L4DFrame:
+        if torch.is_tensor(time):
+            time = float(time.reshape(-1)[0])          # same host sync as lidar4d.py:143
+        return _capi.make_frame_struct(make_frame(time, self.cfg.num_frames, self.cfg.time_resolution))
+
+
+class _RenderFn(torch.autograd.Function):
+    """Fused render forward / backward.  Parameters are passed as inputs so that
+    autograd routes their gradients; the kernels read the staged working set."""
+
+    @staticmethod
+    def forward(ctx, eng: _Engine, rays_o, rays_d, frame, S, perturb, seed, ray_offset, want_weights, train, *params):
+        lib = eng._lib()
+        N = rays_o.shape[0]
+        dev = rays_o.device
+        depth = torch.empty(N, device=dev)
+        image = torch.empty(N, 2, device=dev)
+        wsum = torch.empty(N, device=dev)
+        weights = torch.empty(N, S, device=dev) if want_weights else None
+        zvals = torch.empty(N, S, device=dev) if want_weights else None
+        rays = _capi.L4DRays()
+        rays.rays_o, rays.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
+        rays.n_rays, rays.n_steps, rays.perturb = N, S, int(bool(perturb))
+        rays.seed, rays.ray_offset = int(seed), int(ray_offset)
+        saved, nsaved = None, 0
+        if train:
+            nsaved = lib.l4d_saved_bytes(C.byref(eng.ccfg), N, S)
+            saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.l4d_render_forward(
+                C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(frame), C.byref(rays),
+                depth.data_ptr(), image.data_ptr(), wsum.data_ptr(),
+                weights.data_ptr() if want_weights else None, zvals.data_ptr() if want_weights else None,
+                saved.data_ptr() if train else None, nsaved, eng.stream())
+        _capi.check(lib, rc, "l4d_render_forward")
+        eng.n_launches += 1
+        ctx.eng, ctx.frame, ctx.rays_args = eng, frame, (N, S, int(bool(perturb)), int(seed), int(ray_offset))
+        ctx.saved, ctx.nsaved = saved, nsaved
+        ctx.rays_o, ctx.rays_d = rays_o, rays_d
+        ctx.staged = eng.staged
+        ctx.want_weights = want_weights
+        if want_weights:
+            ctx.mark_non_differentiable(zvals)
+            return depth, image, wsum, weights, zvals
+        return depth, image, wsum
+
+    @staticmethod
+    def backward(ctx, g_depth, g_image, g_wsum, *rest):
+        eng = ctx.eng
+        lib = eng._lib()
+        if ctx.saved is None:
+            raise RuntimeError("render was run without saving activations (no_grad / eval)")
+        N, S, perturb, seed, ray_offset = ctx.rays_args
+        dev = ctx.rays_o.device
+        g_weights = rest[0] if (ctx.want_weights and len(rest) > 0) else None
+        z = lambda t, shape: (torch.zeros(shape, device=dev) if t is None else t.contiguous().float())
+        g_depth, g_image = z(g_depth, (N,)), z(g_image, (N, 2))
+        g_wsum = None if g_wsum is None else g_wsum.contiguous().float()
+        g_weights = None if g_weights is None else g_weights.contiguous().float()
+        flat, views = eng.new_grad_arena()
+        tab = eng.grad_table(views)
+        nwork = lib.l4d_grad_work_bytes(C.byref(eng.ccfg))
+        work = torch.zeros(nwork, dtype=torch.uint8, device=dev)
+        rays = _capi.L4DRays()
+        rays.rays_o, rays.rays_d = ctx.rays_o.data_ptr(), ctx.rays_d.data_ptr()
+        rays.n_rays, rays.n_steps, rays.perturb, rays.seed, rays.ray_offset = N, S, perturb, seed, ray_offset
+        with torch.cuda.device(dev):
+            rc = lib.l4d_render_backward(
+                C.byref(eng.ccfg), ctx.staged.data_ptr(), C.byref(ctx.frame), C.byref(rays),
+                ctx.saved.data_ptr(), ctx.nsaved, g_depth.data_ptr(), g_image.data_ptr(),
+                g_wsum.data_ptr() if g_wsum is not None else None,
+                g_weights.data_ptr() if g_weights is not None else None,
+                C.byref(tab), work.data_ptr(), nwork, eng.stream())
+            _capi.check(lib, rc, "l4d_render_backward")
+            rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), nwork, C.byref(tab), eng.stream())
+            _capi.check(lib, rc, "l4d_unstage_grads")
+        eng.n_launches += 1 + 6 * eng.cfg.n_levels_plane + 11
+        eng.owner._last_grad_arena = flat
+        ctx.saved = None
+        return (None,) * 10 + tuple(views[n] for n in eng.names)
+
+
+class _FlowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng: _Engine, x, frame, train, *params):
+        lib = eng._lib()
+        n = x.shape[0]
+        flow = torch.empty(n, 6, device=x.device)
+        saved = torch.empty(16, n, device=x.device) if train else None
+        with torch.cuda.device(x.device):
+            rc = lib.l4d_flow_forward(C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(frame), x.data_ptr(), n,
+                                      flow.data_ptr(), saved.data_ptr() if train else None, eng.stream())
+        _capi.check(lib, rc, "l4d_flow_forward")
+        eng.n_launches += 1
+        ctx.eng, ctx.frame, ctx.x, ctx.saved, ctx.staged = eng, frame, x, saved, eng.staged
+        return flow
+
+    @staticmethod
+    def backward(ctx, g_flow):
+        eng = ctx.eng
+        lib = eng._lib()
+        if ctx.saved is None:
+            raise RuntimeError("flow was run without saving activations")
+        x = ctx.x
+        n = x.shape[0]
+        g_flow = g_flow.contiguous().float()
+        flat, views = eng.new_grad_arena()
+        tab = eng.grad_table(views)
+        nwork = lib.l4d_grad_work_bytes(C.byref(eng.ccfg))
+        work = torch.zeros(nwork, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.l4d_flow_backward(C.byref(eng.ccfg), ctx.staged.data_ptr(), C.byref(ctx.frame), x.data_ptr(), n,
+                                       ctx.saved.data_ptr(), g_flow.data_ptr(), C.byref(tab), work.data_ptr(), nwork,
+                                       eng.stream())
+            _capi.check(lib, rc, "l4d_flow_backward")
+            rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), nwork, C.byref(tab), eng.stream())
+            _capi.check(lib, rc, "l4d_unstage_grads")
+        eng.n_launches += 1 + 6 * eng.cfg.n_levels_plane + 11
+        flow_names = {"flow_net.grid_enc.params", "flow_net.mlp.0.weight", "flow_net.mlp.2.weight", "flow_net.mlp.4.weight"}
+        return (None,) * 4 + tuple(views[n] if n in flow_names else None for n in eng.names)
+
+
+# =============================================================================
+# public modules
+# =============================================================================
+class LiDAR_Renderer(nn.Module):
+    """model/renderer.py:13-186 API."""
+
+    def __init__(self, bound=1, near_lidar=0.01, far_lidar=0.81, density_scale=1, active_sensor=False):
+        super().__init__()
+        self.bound = bound
+        self.near_lidar = near_lidar
+        self.far_lidar = far_lidar
+        self.density_scale = density_scale
+        self.active_sensor = active_sensor
+        aabb = torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound])
+        self.register_buffer("aabb", aabb)
+
+    def forward(self, x, d):
+        raise NotImplementedError()
+
+    def run(self, rays_o, rays_d, time, num_steps=768, perturb=False, **kwargs):
+        raise NotImplementedError()
+
+    def render(self, rays_o, rays_d, time, staged=False, max_ray_batch=4096, **kwargs):
+        """renderer.py:142-186.  `staged` keeps the reference's chunked contract
+        (only depth/image returned); chunks may be larger here because nothing of
+        size [N*S, C] is materialised."""
+        B, N = rays_o.shape[:2]
+        device = rays_o.device
+        if staged:
+            depth = torch.empty((B, N), device=device)
+            image = torch.empty((B, N, self.out_lidar_dim), device=device)
+            for b in range(B):
+                head = 0
+                while head < N:
+                    tail = min(head + max_ray_batch, N)
+                    r = self.run(rays_o[b:b + 1, head:tail], rays_d[b:b + 1, head:tail], time[b:b + 1], **kwargs)
+                    depth[b:b + 1, head:tail] = r["depth_lidar"]
+                    image[b:b + 1, head:tail] = r["image_lidar"]
+                    head += max_ray_batch
+            return {"depth_lidar": depth, "image_lidar": image}
+        return self.run(rays_o, rays_d, time, **kwargs)
+
+
+class LiDAR4D(LiDAR_Renderer):
+    def __init__(self, min_resolution=32, base_resolution=512, max_resolution=32768, time_resolution=8,
+                 n_levels_plane=4, n_features_per_level_plane=8, n_levels_hash=8, n_features_per_level_hash=4,
+                 log2_hashmap_size=19, num_layers_flow=3, hidden_dim_flow=64, num_layers_sigma=2,
+                 hidden_dim_sigma=64, geo_feat_dim=15, num_layers_lidar=3, hidden_dim_lidar=64, out_lidar_dim=2,
+                 num_frames=51, bound=1, unet: Optional[nn.Module] = None, **kwargs):
+        renderer_kw = {k: kwargs[k] for k in ("near_lidar", "far_lidar", "density_scale", "active_sensor") if k in kwargs}
+        super().__init__(bound, **renderer_kw)
+        self.cfg = FieldConfig(
+            min_resolution=min_resolution, base_resolution=base_resolution, max_resolution=max_resolution,
+            time_resolution=time_resolution, n_levels_plane=n_levels_plane,
+            n_features_per_level_plane=n_features_per_level_plane, n_levels_hash=n_levels_hash,
+            n_features_per_level_hash=n_features_per_level_hash, log2_hashmap_size=log2_hashmap_size,
+            hash_size_dynamic=tuple(kwargs.get("hash_size_dynamic", (15, 13, 13))),
+            num_layers_flow=num_layers_flow, hidden_dim_flow=hidden_dim_flow, num_layers_sigma=num_layers_sigma,
+            hidden_dim_sigma=hidden_dim_sigma, geo_feat_dim=geo_feat_dim, num_layers_lidar=num_layers_lidar,
+            hidden_dim_lidar=hidden_dim_lidar, out_lidar_dim=out_lidar_dim, num_frames=num_frames, bound=float(bound),
+            near_lidar=float(self.near_lidar), far_lidar=float(self.far_lidar), density_scale=float(self.density_scale),
+            active_sensor=bool(self.active_sensor),
+            **{k: kwargs[k] for k in ("flow_base_resolution", "flow_max_resolution", "flow_log2_hashmap_size") if k in kwargs})
+        c = self.cfg
+        c.validate()
+        self.out_lidar_dim = out_lidar_dim
+        self.num_frames = num_frames
+
+        self.planes_encoder = _Planes4D(c)
+        self.hash_encoder = _HashGrid4D(c)
+        self.view_encoder = _TcnnParams(0, c.view_dim, "empty")
+        self.flow_net = _FlowField(c)
+        self.sigma_net = _TcnnParams(c.mlp_param_count(c.sigma_in_pad, 64, 1), 1 + geo_feat_dim, "mlp",
+                                     dims=[c.sigma_in_pad, 64, 16])
+        self.intensity_net = _TcnnParams(c.mlp_param_count(c.attr_in_pad, 64, 2), 1, "mlp", dims=[c.attr_in_pad, 64, 64, 16])
+        self.raydrop_net = _TcnnParams(c.mlp_param_count(c.attr_in_pad, 64, 2), 1, "mlp", dims=[c.attr_in_pad, 64, 64, 16])
+        # U-Net ray-drop refinement is a per-image post-process outside the hot path;
+        # callers that need it pass the reference's module in (model/unet.py), its state_dict keys stay `unet.*`.
+        self.unet = unet if unet is not None else nn.Identity()
+
+        self.materialize_weights = True    # return `weights` / `z_vals` like renderer.py:134-140
+        self.jitter_seed = 0
+        self._jitter_calls = 0
+        self._last_grad_arena = None
+        self._engine = _Engine(self)
+
+    # ---- nn.Module plumbing -----------------------------------------------------------------
+    def forward(self, x, d, t):
+        pass
+
+    def _params_list(self) -> List[torch.Tensor]:
+        ts = self._engine.tensors()
+        return [ts[n] for n in self._engine.names]
+
+    # ---- LiDAR_Renderer.run (renderer.py:44-140) -----------------------------------------------
+    def run(self, rays_o, rays_d, time, num_steps=768, perturb=False, ray_offset=0, **kwargs):
+        eng = self._engine
+        prefix = rays_o.shape[:-1]
+        ro = rays_o.detach().contiguous().view(-1, 3).float()
+        rd = rays_d.detach().contiguous().view(-1, 3).float()
+        eng._require_cuda(ro, rd)
+        eng.ensure_staged()
+        frame = eng.frame(time)
+        params = self._params_list()
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        seed = 0
+        if perturb:
+            seed = self.jitter_seed + self._jitter_calls
+            self._jitter_calls += 1
+        want_w = bool(self.materialize_weights)
+        out = _RenderFn.apply(eng, ro, rd, frame, int(num_steps), bool(perturb), seed, int(ray_offset), want_w, train, *params)
+        res = {"depth_lidar": out[0].view(*prefix), "image_lidar": out[1].view(*prefix, self.out_lidar_dim),
+               "weights_sum_lidar": out[2]}
+        if want_w:
+            res["weights"], res["z_vals"] = out[3], out[4]
+        return res
+
+    # ---- LiDAR4D.flow (lidar4d.py:124-137) -------------------------------------------------------
+    def flow(self, x, t):
+        eng = self._engine
+        x = x.detach().contiguous().view(-1, 3).float()
+        eng._require_cuda(x)
+        eng.ensure_staged()
+        frame = eng.frame(t)
+        params = self._params_list()
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        fl = _FlowFn.apply(eng, x, frame, train, *params)
+        return {"forward": fl[:, :3], "backward": fl[:, 3:]}
+
+    # ---- LiDAR4D.density (lidar4d.py:139-188), inference / parity only ---------------------------
+    @torch.no_grad()
+    def density(self, x, t=None, return_features: bool = False):
+        eng = self._engine
+        lib = eng._lib()
+        x = x.detach().contiguous().view(-1, 3).float()
+        eng._require_cuda(x)
+        eng.ensure_staged()
+        frame = eng.frame(t)
+        n = x.shape[0]
+        sigma = torch.empty(n, device=x.device)
+        geo = torch.empty(n, 15, device=x.device)
+        feats = torch.empty(n, self.cfg.sigma_in_dim, device=x.device) if return_features else None
+        flow = torch.empty(n, 6, device=x.device) if return_features else None
+        with torch.cuda.device(x.device):
+            rc = lib.l4d_density_forward(C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(frame), x.data_ptr(), n,
+                                         sigma.data_ptr(), geo.data_ptr(),
+                                         feats.data_ptr() if return_features else None,
+                                         flow.data_ptr() if return_features else None, eng.stream())
+        _capi.check(lib, rc, "l4d_density_forward")
+        eng.n_launches += 1
+        out = {"sigma": sigma, "geo_feat": geo}
+        if return_features:
+            out.update(features=feats, flow=flow)
+        return out
+
+    def attribute(self, x, d, mask=None, geo_feat=None, **kwargs):
+        raise NotImplementedError("attribute heads are fused into render()/run(); see lidar4d_b200/csrc/l4d_core.cuh")
+
+    @torch.no_grad()
+    def hash_indices(self, grid_id: int, level: int, x: torch.Tensor):
+        """Parity hook: uint32 corner indices + weights of one level (grid_id 0 static, 1-3 dynamic, 4 flow)."""
+        eng = self._engine
+        lib = eng._lib()
+        x = x.detach().contiguous().float()
+        eng._require_cuda(x)
+        n, D = x.shape
+        idx = torch.empty(n, 1 << D, dtype=torch.int32, device=x.device)
+        w = torch.empty(n, 1 << D, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.l4d_hash_indices(C.byref(eng.ccfg), grid_id, level, x.data_ptr(), n, idx.data_ptr(), w.data_ptr(),
+                                      eng.stream())
+        _capi.check(lib, rc, "l4d_hash_indices")
+        eng.n_launches += 1
+        return idx, w
+
+    # ---- optimizer utils (lidar4d.py:226-237) ----------------------------------------------------
+    def get_params(self, lr):
+        return [
+            {"params": self.planes_encoder.parameters(), "lr": lr},
+            {"params": self.hash_encoder.parameters(), "lr": lr},
+            {"params": self.view_encoder.parameters(), "lr": lr},
+            {"params": self.flow_net.parameters(), "lr": 0.1 * lr},
+            {"params": self.sigma_net.parameters(), "lr": 0.1 * lr},
+            {"params": self.intensity_net.parameters(), "lr": 0.1 * lr},
+            {"params": self.raydrop_net.parameters(), "lr": 0.1 * lr},
+        ]
+
+    @property
+    def gpu_launches(self) -> int:
+        return self._engine.n_launches

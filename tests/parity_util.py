@@ -1,0 +1,60 @@
+"""Shared helpers of the parity tests (test infrastructure)."""
+import numpy as np
+import torch
+
+from lidar4d_b200.geometry import FieldConfig
+
+SMALL = dict(min_resolution=8, base_resolution=16, max_resolution=512, time_resolution=8,
+             n_levels_hash=4, log2_hashmap_size=12, num_frames=6, near_lidar=0.0105, far_lidar=0.851,
+             hash_size_dynamic=(9, 8, 8), flow_base_resolution=8, flow_max_resolution=256,
+             flow_log2_hashmap_size=10)
+
+
+def small_config(**over) -> FieldConfig:
+    kw = dict(SMALL)
+    kw.update(over)
+    return FieldConfig(**kw)
+
+
+def rel_err(a, b) -> float:
+    """max |a-b| / max |b| (the 1e-4 'rel fp32' bar of BASELINE.json:north_star)."""
+    a = torch.as_tensor(a).detach().double().reshape(-1).cpu()
+    b = torch.as_tensor(b).detach().double().reshape(-1).cpu()
+    if a.numel() == 0:
+        return 0.0
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def make_surface_like(oracle, gain: float = 1.5):
+    """Sharpen the density so that most samples fall below the w>1e-4 attribute
+    mask (SURVEY.md 8(d) 'surface-like' regime): make the sigma row of the output
+    layer positive (hidden units are >= 0) and scale it."""
+    c = oracle.cfg
+    with torch.no_grad():
+        p = oracle.p("sigma_net.params")
+        off = 64 * c.sigma_in_pad
+        p[off:off + 64] = p[off:off + 64].abs() * gain
+    return oracle
+
+
+def cuda_model_from_oracle(oracle, device="cuda"):
+    """CUDA LiDAR4D with the oracle's parameters (state_dict round trip)."""
+    from lidar4d_b200 import LiDAR4D
+    c = oracle.cfg
+    m = LiDAR4D(min_resolution=c.min_resolution, base_resolution=c.base_resolution, max_resolution=c.max_resolution,
+                time_resolution=c.time_resolution, n_levels_plane=c.n_levels_plane, n_levels_hash=c.n_levels_hash,
+                log2_hashmap_size=c.log2_hashmap_size, num_frames=c.num_frames, bound=c.bound,
+                near_lidar=c.near_lidar, far_lidar=c.far_lidar, density_scale=c.density_scale,
+                active_sensor=c.active_sensor, hash_size_dynamic=c.hash_size_dynamic,
+                flow_base_resolution=c.flow_base_resolution, flow_max_resolution=c.flow_max_resolution,
+                flow_log2_hashmap_size=c.flow_log2_hashmap_size)
+    res = m.load_state_dict(oracle.ref_state_dict(), strict=False)
+    assert not res.missing_keys and not res.unexpected_keys, res
+    return m.to(device)
+
+
+def test_rays(H=3, W=8, origin=(0.1, -0.05, 0.02)):
+    from lidar4d_b200.rays import lidar_rays
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, 3] = origin
+    return lidar_rays(pose, H, W)
