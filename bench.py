@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py - training rays/s of the LiDAR4D hot path on B200 (driver contract in the task brief).
+
+Workload (BASELINE.json configs[1]): synthetic KITTI-360-like sweep of 64x1024 rays x 768 samples,
+L=16 4D hash + 6 hex-planes + flow field, 50-frame straight trajectory.
+One "step" = one optimiser step on one 65,536-ray sweep of one frame: forward + backward of the
+fused kernels over the sweep (in ray chunks, gradients accumulated), one Adam step with the
+reference's recipe (main_lidar4d.py:298-300) and the re-staging of the kernel working set.
+
+  python bench.py [--gpus N --steps K --warmup W]            this repo's CUDA path
+  python bench.py --impl reference [...]                     CPU reference arm: the oracle port of the
+                                                             reference python path (tiny-cuda-nn cannot run
+                                                             anywhere here), bounded sample per step
+Under torchrun (N>1) every rank renders its own sweep (weak scaling, rays shard with no data-path
+collective) and the flat gradient arena is all-reduced once per step over NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H_SWEEP, W_SWEEP, S_STEPS, N_FRAMES = 64, 1024, 768, 50
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--levels", type=int, default=16, help="n_levels_hash (BASELINE configs[1]: L=16; reference default 8)")
+    ap.add_argument("--ray-batch", type=int, default=8192, help="rays per fused forward/backward launch")
+    ap.add_argument("--rays", type=int, default=H_SWEEP * W_SWEEP, help="rays per step (sweep size)")
+    ap.add_argument("--cpu-rays", type=int, default=128, help="rays of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def model_kwargs(levels):
+    return dict(n_levels_hash=levels, num_frames=N_FRAMES + 1, near_lidar=0.0105, far_lidar=0.851)
+
+
+def randomize(model, seed=0):
+    """SURVEY.md 8(d) parameters: hash tables U(-0.5,0.5), planes reference init + N(0,0.1), flow head N(0,1e-3)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if "hash" in k or "grid_enc" in k:
+                n = p.numel()
+                chunk = torch.rand(min(n, 1 << 22), generator=g) - 0.5
+                reps = (n + chunk.numel() - 1) // chunk.numel()
+                p.copy_(chunk.repeat(reps)[:n].view_as(p).to(p.device))
+            elif "planes" in k:
+                p.add_((torch.randn(p.shape, generator=g) * 0.1).to(p.device))
+
+
+def algorithmic_bytes(cfg):
+    """Per-sample algorithmic bytes (restated for this configuration in DESIGN.md)."""
+    L = cfg.n_levels_hash
+    fwd = L * 8 * 8 + 3 * (3 * 2 * L * 4 * 8) + 8 * 8 * 16 + 4 * 3 * 4 * 32 + 3 * (4 * 3 * 4 * 32)
+    scatter = L * 8 * 16 + 3 * 2 * L * 4 * 16 + 8 * 8 * 32 + (4 * 3 * 4 * 32) * 4
+    bwd = 2 * scatter + 4 * (4 * 3 * 4 * 32) + 4 * (cfg.sigma_in_dim + 16 + 3)
+    return fwd, bwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            sm = [float(r[0]) for r in rows]
+            out["samples"] = len(sm)
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][1])
+                out["power_w_max"] = max(float(r[2]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for i, n in enumerate(names):
+                    if any("Active" in r[3 + i] and "Not" not in r[3 + i] for r in rows):
+                        out["reasons"].append(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# =============================================================================
+# CPU arm: the oracle port of the reference python path
+# =============================================================================
+def cpu_reference_step(orc, opt, ro, rd, t, seed):
+    from oracle import lidar4d_oracle as O  # noqa: F401  (bench cpu_baseline / --impl reference leg only)
+    opt.zero_grad()
+    out = orc.render(torch.from_numpy(ro), torch.from_numpy(rd), t, num_steps=S_STEPS, perturb=True, seed=seed)
+    loss = (out["depth_lidar"] - 0.3).abs().mean() + ((out["image_lidar"] - 0.5) ** 2).mean()
+    loss.backward()
+    opt.step()
+    return float(loss)
+
+
+def build_oracle(levels):
+    from oracle import lidar4d_oracle as O
+    from lidar4d_b200.geometry import FieldConfig
+    cfg = FieldConfig(**model_kwargs(levels))
+    torch.manual_seed(0)
+    orc = O.OracleLiDAR4D(cfg)
+    O.randomize_parameters(orc, seed=0, flow_last_std=1e-3)
+    opt = torch.optim.Adam(orc.parameters(), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    return orc, opt
+
+
+def cpu_sample(levels, n_rays, repeats=1):
+    """rays/s of the oracle on this box's host cores for a bounded sample of the workload."""
+    from lidar4d_b200.rays import synthetic_sweep
+    orc, opt = build_oracle(levels)
+    ro, rd, t = synthetic_sweep(7, N_FRAMES, H_SWEEP, W_SWEEP)
+    sel = np.linspace(0, ro.shape[0] - 1, n_rays).astype(np.int64)
+    cpu_reference_step(orc, opt, ro[sel], rd[sel], float(t), 0)         # warm-up
+    ts = []
+    for i in range(repeats):
+        t0 = time.perf_counter()
+        cpu_reference_step(orc, opt, ro[sel], rd[sel], float(t), i + 1)
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.median(ts))
+    return n_rays / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; tiny-cuda-nn is absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    from lidar4d_b200.rays import synthetic_sweep
+    orc, opt = build_oracle(args.levels)
+    n = args.cpu_rays
+    ts = []
+    for i in range(args.warmup + args.steps):
+        ro, rd, t = synthetic_sweep(i % N_FRAMES, N_FRAMES, H_SWEEP, W_SWEEP)
+        sel = np.linspace(0, ro.shape[0] - 1, n).astype(np.int64)
+        t0 = time.perf_counter()
+        cpu_reference_step(orc, opt, ro[sel], rd[sel], float(t), i)
+        if i >= args.warmup:
+            ts.append(time.perf_counter() - t0)
+    total = float(sum(ts))
+    val = n * args.steps / total
+    sample = f"{n} rays x {S_STEPS} samples fwd+bwd+Adam per step (bounded sample of the 65,536-ray sweep), fp32"
+    line = {
+        "impl": "reference", "metric": "training rays/sec at 64x1024 rays x 768 samples", "value": val, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, note="CPU: oracle port of the reference python path on the tcnn spec"),
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, note=None):
+    c = {"workload": f"synthetic KITTI-360-like sweep {H_SWEEP}x{W_SWEEP} rays x {S_STEPS} samples, "
+                     f"L={args.levels} 4D hash (2^19 static, 2^15/2^13/2^13 x8 time slices) + 6 hex-planes x4 scales + flow field, "
+                     f"{N_FRAMES} frames",
+         "rays_per_step": args.rays, "ray_batch": args.ray_batch, "n_levels_hash": args.levels,
+         "parallelism": f"ray-sharded dp{args.gpus}",
+         "l2": "inputs larger than L2: fp16/fp32 working set > 126 MB plus > 1 GB of saved activations streamed per step"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# =============================================================================
+# GPU arm
+# =============================================================================
+def run_b200(args):
+    import torch.distributed as dist
+    from lidar4d_b200 import LiDAR4D
+    from lidar4d_b200.rays import synthetic_sweep
+    from lidar4d_b200.parallel import RayShardedDP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    model = LiDAR4D(**model_kwargs(args.levels)).to(dev)
+    randomize(model, 0)
+    model.materialize_weights = False            # weights/z_vals are only read by --urf_loss (runner.py:256-276)
+    dp = RayShardedDP(model, world_size=world, rank=rank)
+    opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True)
+    n_rays, rb = args.rays, args.ray_batch
+
+    # host-side inputs in pinned memory (one sweep per frame), targets on the host as well
+    frames = []
+    for k in range(min(N_FRAMES, args.warmup + args.steps + 1)):
+        ro, rd, t = synthetic_sweep((k * world + rank) % N_FRAMES, N_FRAMES, H_SWEEP, W_SWEEP)
+        ro, rd = ro[:n_rays], rd[:n_rays]
+        frames.append((torch.from_numpy(ro).pin_memory(), torch.from_numpy(rd).pin_memory(), float(t)))
+    host_out = torch.empty(n_rays, 3).pin_memory()
+
+    def step(i, e2e):
+        ro_h, rd_h, t = frames[i % len(frames)]
+        if e2e:
+            ro_d, rd_d = ro_h.to(dev, non_blocking=True), rd_h.to(dev, non_blocking=True)
+            step.cache = (ro_d, rd_d)
+        else:
+            if getattr(step, "resident", None) is None or step.resident[0] != i % len(frames):
+                step.resident = (i % len(frames), ro_h.to(dev), rd_h.to(dev))
+            ro_d, rd_d = step.resident[1], step.resident[2]
+        opt.zero_grad(set_to_none=True)
+        tot = torch.zeros((), device=dev)
+        outs = []
+        for h in range(0, n_rays, rb):
+            out = model.render(ro_d[None, h:h + rb], rd_d[None, h:h + rb], t, staged=False, num_steps=S_STEPS,
+                               perturb=True, ray_offset=rank * n_rays + h)
+            loss = ((out["depth_lidar"] - 0.3).abs().sum() + ((out["image_lidar"] - 0.5) ** 2).sum()) / (n_rays * world)
+            loss.backward()
+            tot += loss.detach()
+            if e2e:
+                outs.append(torch.cat([out["depth_lidar"].detach().view(-1, 1), out["image_lidar"].detach().view(-1, 2)], 1))
+        dp.allreduce_grads()
+        opt.step()
+        model._engine.ensure_staged()
+        if e2e:
+            host_out.copy_(torch.cat(outs, 0), non_blocking=True)
+            return float(tot)            # device->host read of the step's loss (sync)
+        return tot
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e, n_steps, base):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.gpu_launches
+        ev0.record()
+        for i in range(n_steps):
+            step(base + i, e2e)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tm = torch.tensor([ms], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm)
+        return ms, model.gpu_launches - l0
+
+    for i in range(args.warmup):
+        step(i, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(False, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else {}
+    step(0, True)                                  # warm the e2e path (pinned copies)
+    ms_e2e, _ = timed(True, args.steps, args.warmup)
+
+    # ---- per-kernel durations for the roofline (CUDA events on the launching stream) ----
+    eng = model._engine
+    eng.timing = {"fwd": [], "bwd": []}
+    for i in range(2):
+        step(args.warmup + i, False)
+    torch.cuda.synchronize()
+    t_f = [a.elapsed_time(b) for a, b in eng.timing["fwd"]]
+    t_b = [a.elapsed_time(b) for a, b in eng.timing["bwd"]]
+    eng.timing = None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    fwd_b, bwd_b = algorithmic_bytes(model.cfg)
+    peak, peak_src = peaks()
+    samples_per_launch = min(rb, n_rays) * S_STEPS
+    kern = {}
+    for name, ts, b in (("k_render_fwd", t_f, fwd_b), ("k_render_bwd", t_b, bwd_b)):
+        if ts:
+            avg = float(np.mean(ts))
+            kern[name] = {"avg_ms": avg, "launches_timed": len(ts), "alg_bytes_per_sample": b,
+                          "achieved_gbs": b * samples_per_launch / (avg * 1e-3) / 1e9}
+    dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src, "kernels": kern,
+                    "note": "algorithmic bytes (DESIGN.md); tables fit the 126 MB L2 so dram bytes (profiles/) are lower"}
+    total_rays = n_rays * world * args.steps
+    value = total_rays / (ms * 1e-3)
+    line = {
+        "metric": "training rays/sec at 64x1024 rays x 768 samples", "value": value, "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 tables / fp32 planes, MLPs, compositing and gradients", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n_rays * 6 * 4,
+                "d2h_bytes_per_step": n_rays * 3 * 4 + 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        torch.set_num_threads(os.cpu_count() or 1)
+        v, dt = cpu_sample(args.levels, args.cpu_rays)
+        line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{args.cpu_rays} rays x {S_STEPS} samples fwd+bwd+Adam ({dt:.1f} s), oracle port of the "
+                                          "reference python path (tiny-cuda-nn itself is CUDA-only and absent)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -118,6 +118,7 @@ class _Engine:
         self.staged = None
         self._stamp = None
         self.n_launches = 0        # kernels of this library launched so far (bench "gpu_launches")
+        self.timing = None         # {'fwd': [(ev0, ev1)], 'bwd': [...]}: CUDA events around the fused kernels
 
     def _lib(self):
         if self.lib is None:
@@ -142,6 +143,13 @@ class _Engine:
 
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device()).cuda_stream
+
+    def _events(self, kind):
+        if self.timing is None:
+            return None
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self.timing[kind].append(ev)
+        return ev
 
     def ensure_staged(self):
         """Refresh the fp16 / channels-last / transposed working set when any
@@ -209,12 +217,15 @@ class _RenderFn(torch.autograd.Function):
         if train:
             nsaved = lib.l4d_saved_bytes(C.byref(eng.ccfg), N, S)
             saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
+        ev = eng._events("fwd")
         with torch.cuda.device(dev):
+            if ev: ev[0].record()
             rc = lib.l4d_render_forward(
                 C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(frame), C.byref(rays),
                 depth.data_ptr(), image.data_ptr(), wsum.data_ptr(),
                 weights.data_ptr() if want_weights else None, zvals.data_ptr() if want_weights else None,
                 saved.data_ptr() if train else None, nsaved, eng.stream())
+            if ev: ev[1].record()
         _capi.check(lib, rc, "l4d_render_forward")
         eng.n_launches += 1
         ctx.eng, ctx.frame, ctx.rays_args = eng, frame, (N, S, int(bool(perturb)), int(seed), int(ray_offset))
@@ -247,13 +258,16 @@ class _RenderFn(torch.autograd.Function):
         rays = _capi.L4DRays()
         rays.rays_o, rays.rays_d = ctx.rays_o.data_ptr(), ctx.rays_d.data_ptr()
         rays.n_rays, rays.n_steps, rays.perturb, rays.seed, rays.ray_offset = N, S, perturb, seed, ray_offset
+        ev = eng._events("bwd")
         with torch.cuda.device(dev):
+            if ev: ev[0].record()
             rc = lib.l4d_render_backward(
                 C.byref(eng.ccfg), ctx.staged.data_ptr(), C.byref(ctx.frame), C.byref(rays),
                 ctx.saved.data_ptr(), ctx.nsaved, g_depth.data_ptr(), g_image.data_ptr(),
                 g_wsum.data_ptr() if g_wsum is not None else None,
                 g_weights.data_ptr() if g_weights is not None else None,
                 C.byref(tab), work.data_ptr(), nwork, eng.stream())
+            if ev: ev[1].record()
             _capi.check(lib, rc, "l4d_render_backward")
             rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), nwork, C.byref(tab), eng.stream())
             _capi.check(lib, rc, "l4d_unstage_grads")
