@@ -32,6 +32,10 @@ sys.path.insert(0, ROOT)
 H_SWEEP, W_SWEEP, S_STEPS, N_FRAMES = 64, 1024, 768, 50
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -295,13 +299,18 @@ def run_b200(args):
             ms = float(tm)
         return ms, model.gpu_launches - l0
 
+    log(f"model ready (L={args.levels}), {n_rays} rays/step in launches of {rb}")
     for i in range(args.warmup):
+        tw = time.perf_counter()
         step(i, False)
+        torch.cuda.synchronize()
+        log(f"warm-up step {i}: {time.perf_counter() - tw:.2f} s")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms, launches = timed(False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else {}
+    log(f"timed: {ms / args.steps:.1f} ms/step")
     step(0, True)                                  # warm the e2e path (pinned copies)
     ms_e2e, _ = timed(True, args.steps, args.warmup)
 
@@ -346,6 +355,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": n_rays * 3 * 4 + 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
+    log(f"e2e {ms_e2e / args.steps:.1f} ms/step; kernels {kern}")
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
         v, dt = cpu_sample(args.levels, args.cpu_rays)

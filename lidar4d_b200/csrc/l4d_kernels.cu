@@ -11,6 +11,7 @@
 #include "l4d_bwd.cuh"
 #include "l4d_core.cuh"
 #include "l4d_host.h"
+#include "l4d_tc.cuh"
 
 // =============================================================================
 // error plumbing
@@ -884,6 +885,18 @@ extern "C" int l4d_density_forward(const L4DConfig* cfg, const void* staged, con
   const size_t smem = 64 * L4D_NT * sizeof(float);
   L4D_CUDA(cudaFuncSetAttribute(k_density<L4D_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_density<L4D_NT><<<nblk(n, L4D_NT), L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+// tcgen05 self-test: C[128][N] = A[128][K] (fp16) * B[N][K]^T (fp16), fp32 accumulate in TMEM
+extern "C" int l4d_tc_selftest(const void* A, const void* B, float* Cout, uint32_t N, uint32_t K, void* stream) {
+  if (!A || !B || !Cout) return l4d_fail(L4D_EINVAL, "null pointer");
+  if (N < 16 || N > 256 || N % 16 || K < 16 || K % 16 || K > 512) return l4d_fail(L4D_EINVAL, "need N%16==0 in [16,256], K%16==0 in [16,512]");
+  const size_t smem = (size_t)(K / 8) * (128 + N) * 16 + 1024;
+  L4D_CUDA(cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tc_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(B),
+                                                        Cout, (int)N, (int)K);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }

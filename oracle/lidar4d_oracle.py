@@ -95,7 +95,7 @@ def working_table(params: torch.Tensor, table_dtype: str) -> torch.Tensor:
     master (tcnn keeps fp32 masters and casts per call [tcnn-ext])."""
     if table_dtype == "fp32":
         return params
-    q = params.detach().to(torch.float16).to(params.dtype)
+    q = params.detach().to(torch.float32).to(torch.float16).to(params.dtype)
     return params + (q - params.detach())
 
 
@@ -213,6 +213,7 @@ class OracleLiDAR4D(nn.Module):
         c = self.cfg
         c.validate()
         self.table_dtype = table_dtype
+        self.cd = torch.float32          # compute dtype; float64 = "truth" mode (see to_float64)
         self.g_static = c.static_grid()
         self.g_dynamic = [c.dynamic_grid(p) for p in range(3)]
         self.g_flow = c.flow_grid()
@@ -266,6 +267,17 @@ class OracleLiDAR4D(nn.Module):
     def p(self, name: str) -> torch.Tensor:
         return self.P[name.replace(".", "/")]
 
+    def to_float64(self) -> "OracleLiDAR4D":
+        """Truth mode: parameters and all smooth arithmetic in float64.  The
+        quantities the spec pins in float32 (sample positions, x01, hash cell
+        selection / corner weights, the frequency-encoding argument, fp16 table
+        rounding) stay exactly as in float32, so this is the infinitely-precise
+        evaluation of the SAME function; use it to tell which of two float32
+        results is the noisy one."""
+        self.double()
+        self.cd = torch.float64
+        return self
+
     def ref_state_dict(self) -> Dict[str, torch.Tensor]:
         """state_dict with the reference's key names."""
         d = {k.replace("/", "."): v.detach().clone() for k, v in self.P.items()}
@@ -297,7 +309,7 @@ class OracleLiDAR4D(nn.Module):
 
     def hash_static(self, x01):
         """hash_field.py:141-144."""
-        return hash_encode(x01, self.p("hash_encoder.hash_static.params"), self.g_static, self.table_dtype)
+        return hash_encode(x01, self.p("hash_encoder.hash_static.params"), self.g_static, self.table_dtype, self.cd)
 
     def hash_dynamic(self, x, q: TimeQuery):
         """hash_field.py:146-158 with HashGridT.forward :76-88."""
@@ -307,11 +319,11 @@ class OracleLiDAR4D(nn.Module):
         for p, (a, b) in enumerate(pairs):
             x2 = x[:, [a, b]]
             name = f"hash_encoder.hash_dynamic.{p}.hash_t.%d.params"
-            f_lo = hash_encode(x2, self.p(name % q.slice_lo), self.g_dynamic[p], self.table_dtype)
+            f_lo = hash_encode(x2, self.p(name % q.slice_lo), self.g_dynamic[p], self.table_dtype, self.cd)
             if q.single:
                 f = f_lo
             else:
-                f_hi = hash_encode(x2, self.p(name % q.slice_hi), self.g_dynamic[p], self.table_dtype)
+                f_hi = hash_encode(x2, self.p(name % q.slice_hi), self.g_dynamic[p], self.table_dtype, self.cd)
                 f = float(q.w_lo) * f_lo + float(q.w_hi) * f_hi
             outs.append(self.interp_t(f, c.n_levels_hash, c.n_features_per_level_hash, q.basis))
         return torch.cat(outs, -1)
@@ -342,7 +354,7 @@ class OracleLiDAR4D(nn.Module):
     def flow_field(self, x01: torch.Tensor, basis) -> torch.Tensor:
         """flow_field.py:113-130: grid -> interpT at the frame time -> 3 bias-free Linear."""
         c = self.cfg
-        e = hash_encode(x01, self.p("flow_net.grid_enc.params"), self.g_flow, self.table_dtype)
+        e = hash_encode(x01, self.p("flow_net.grid_enc.params"), self.g_flow, self.table_dtype, self.cd)
         h = self.interp_t(e, c.flow_n_levels, c.flow_n_features, basis)
         self._dbg_flow_in = h
         h = torch.relu(h @ self.p("flow_net.mlp.0.weight").t())
@@ -353,7 +365,7 @@ class OracleLiDAR4D(nn.Module):
     def flow(self, x: torch.Tensor, t) -> Dict[str, torch.Tensor]:
         """lidar4d.py:124-137."""
         b = self.cfg.bound
-        x01 = (x + b) / (2 * b)
+        x01 = (x.float() + b) / (2 * b)
         fr = make_frame(float(t), self.cfg.num_frames, self.cfg.time_resolution)
         fl = self.flow_field(x01, fr.flow_basis)
         return {"forward": fl[:, :3], "backward": fl[:, 3:]}
@@ -362,7 +374,7 @@ class OracleLiDAR4D(nn.Module):
         """lidar4d.py:139-188."""
         c = self.cfg
         b = c.bound
-        x01 = (x + b) / (2 * b)
+        x01 = ((x.float() + b) / (2 * b)).to(self.cd)      # float32 arithmetic (lidar4d.py:141), then promote
         N = x01.shape[0]
         hash_s = self.hash_static(x01)
         hash_d = self.hash_dynamic(x01, fr.cur)
@@ -400,12 +412,12 @@ class OracleLiDAR4D(nn.Module):
         """lidar4d.py:191-223 (x is unused by the reference's attribute heads)."""
         c = self.cfg
         N = d.shape[0]
-        out = torch.zeros(N, c.out_lidar_dim, dtype=d.dtype)
+        out = torch.zeros(N, c.out_lidar_dim, dtype=self.cd)
         if mask is not None:
             if not bool(mask.any()):
                 return out
             d, geo = d[mask], geo[mask]
-        enc = frequency_encode((d + 1) / 2, c.view_degree)
+        enc = frequency_encode((d.float() + 1) / 2, c.view_degree).to(self.cd)
         inp = torch.cat([enc, geo], -1)
         inten = torch.sigmoid(fused_mlp(inp, self.p("intensity_net.params"), c.attr_in_dim, 1, 64, 2))
         drop = torch.sigmoid(fused_mlp(inp, self.p("raydrop_net.params"), c.attr_in_dim, 1, 64, 2))
@@ -437,8 +449,9 @@ class OracleLiDAR4D(nn.Module):
         xyz = torch.min(torch.max(xyz, self.aabb[:3]), self.aabb[3:])           # :89
         dens = self.density(xyz.reshape(-1, 3), fr, return_features=return_stages)
         sigma = dens["sigma"].view(N, num_steps)
-        deltas = z[:, 1:] - z[:, :-1]                                           # :98
-        deltas = torch.cat([deltas, float(sample_dist) * torch.ones_like(deltas[:, :1])], -1)
+        deltas = z[:, 1:] - z[:, :-1]                                           # :98 (float32 like the reference)
+        deltas = torch.cat([deltas, float(sample_dist) * torch.ones_like(deltas[:, :1])], -1).to(self.cd)
+        z = z.to(self.cd)
         k = 2.0 if c.active_sensor else 1.0
         alphas = 1 - torch.exp(-k * deltas * c.density_scale * sigma)           # :100-102
         shifted = torch.cat([torch.ones_like(alphas[:, :1]), 1 - alphas + 1e-15], -1)

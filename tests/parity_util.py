@@ -58,3 +58,20 @@ def test_rays(H=3, W=8, origin=(0.1, -0.05, 0.02)):
     pose = np.eye(4, dtype=np.float32)
     pose[:3, 3] = origin
     return lidar_rays(pose, H, W)
+
+
+def relu_margin(oracle, stages) -> float:
+    """Smallest |pre-activation| of the ReLU layers that the oracle exposes (flow
+    MLP, sigma MLP).  Gradients are discontinuous where a pre-activation crosses
+    zero, so two correct fp32 implementations can legitimately differ when this
+    margin is at rounding-noise level; parity cases assert a margin first."""
+    c = oracle.cfg
+    with torch.no_grad():
+        fin = stages["flow_in"].float()
+        y1 = fin @ oracle.p("flow_net.mlp.0.weight").float().t()
+        y2 = torch.relu(y1) @ oracle.p("flow_net.mlp.2.weight").float().t()
+        f = stages["features"].float()
+        pad = torch.ones(f.shape[0], c.sigma_in_pad - c.sigma_in_dim)
+        W1 = oracle.p("sigma_net.params")[:64 * c.sigma_in_pad].float().view(64, c.sigma_in_pad)
+        ys = torch.cat([f, pad], -1) @ W1.t()
+        return float(min(y1.abs().min(), y2.abs().min(), ys.abs().min()))

@@ -11,7 +11,7 @@ import torch
 import hostsim_util as H
 from oracle import lidar4d_oracle as O
 from lidar4d_b200.geometry import FieldConfig, make_frame
-from parity_util import small_config, rel_err, make_surface_like, test_rays as _rays
+from parity_util import small_config, rel_err, make_surface_like, relu_margin, test_rays as _rays
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-4   # BASELINE.json north_star: 1e-4 rel fp32
@@ -50,7 +50,14 @@ CASES = [  # time, S, perturb, seed, surface
     (0.0, 150, True, 4, False),      # first frame: no backward neighbour, single slice (t*7 == 0)
     (1.0, 130, True, 5, False),      # last frame: no forward neighbour
     (0.6, 260, True, 6, True),       # surface-like density: most samples masked out of the attribute heads
+    (0.4, 768, True, 27, False),     # the reference's 768 samples/ray: 6 tiles of 128 in the kernels
 ]
+# Gradients of a ReLU network are discontinuous where a pre-activation crosses zero.  With ~1e6
+# pre-activations per case the smallest |y| is ~1e-8, i.e. at fp32 summation-noise level, and two
+# correct fp32 implementations can then disagree on one sample's ReLU mask (observed: seed 7,
+# min|y| = 4.5e-9 -> 2.8e-4 on flow_net.mlp.0.weight while the float64 oracle sides with neither
+# mask a priori).  Cases therefore assert a margin on the oracle side before comparing gradients.
+MIN_RELU_MARGIN = 1e-8
 
 
 @pytest.mark.parametrize("t,S,perturb,seed,surface", CASES)
@@ -59,7 +66,7 @@ def test_render_forward_backward(t, S, perturb, seed, surface):
     if surface:
         make_surface_like(orc)
     hs = H.HostSim(orc)
-    ro, rd = _rays()
+    ro, rd = _rays() if S < 700 else _rays(2, 5)
     N = ro.shape[0]
     ref = orc.render(torch.from_numpy(ro), torch.from_numpy(rd), t, num_steps=S, perturb=perturb, seed=seed,
                      return_stages=True)
@@ -67,6 +74,7 @@ def test_render_forward_backward(t, S, perturb, seed, surface):
     frac = float(ref["mask"].float().mean())
     if surface:
         assert 0.01 < frac < 0.8, frac
+    assert relu_margin(orc, ref) > MIN_RELU_MARGIN, "pick another seed: a ReLU sits on its kink"
     assert np.array_equal(got["z_vals"].numpy(), ref["z_vals"].numpy())          # sampling is bit-exact
     for k, ko in [("depth", "depth_lidar"), ("image", "image_lidar"), ("wsum", "weights_sum_lidar"), ("weights", "weights")]:
         assert rel_err(got[k], ref[ko]) < TOL, k
