@@ -112,6 +112,9 @@ def test_against_reference_golden(dev, name):
             assert rel_err(got[k], fx["grad:" + k]) < TOL, k
     for k in [k[9:] for k in fx.files if k.startswith("gradnorm:")]:
         n_ref = float(fx["gradnorm:" + k])
+        if got.get(k) is None:                     # view_encoder.params: empty tensor, never receives a gradient
+            assert n_ref == 0.0, k
+            continue
         assert abs(float(got[k].double().norm()) - n_ref) <= 1e-4 * n_ref + 1e-12, k
 
 
@@ -161,6 +164,8 @@ def full_model(dev):
                 p.copy_(((torch.rand(p.shape, generator=g) - 0.5)).to(dev))
             elif k.endswith("mlp.4.weight"):
                 p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(dev))
+            elif "planes" in k:      # constant time planes have zero spatial derivative: no gradient would reach the flow net
+                p.add_((torch.randn(p.shape, generator=g) * 0.1).to(dev))
     return m
 
 
