@@ -48,12 +48,7 @@ L4D_HD void l4d_bw_flow_fwd(const DevModel& M, BwSample& s, const float* flow_in
 L4D_HD void l4d_bw_sigma_fwd(const DevModel& M, BwSample& s, const float* feat, size_t stride,
                              float* xb, int xs, float* hidden_out, size_t hs) {
   float acc[L4D_H];
-#pragma unroll
-  for (int k = 0; k < L4D_H; ++k) acc[k] = 0.f;
-  if (s.active) {
-    for (int k = 0; k < (int)M.sigma_in_dim; ++k) l4d_axpy64(acc, feat[(size_t)k * stride], M.sig_w1t + (size_t)k * L4D_H);
-    for (int k = (int)M.sigma_in_dim; k < (int)M.sigma_in_pad; ++k) l4d_axpy64(acc, 1.0f, M.sig_w1t + (size_t)k * L4D_H);
-  }
+  l4d_sigma_hidden_from_feats(M, feat, stride, s.active, acc);
   l4d_relu_store(acc, xb, xs, s.msa, s.msb);
   if (s.active) {
 #pragma unroll
@@ -172,14 +167,37 @@ L4D_HD void l4d_bw_sigma_c(const DevModel& M, const BwSample& s, const float* fe
 }
 
 // ---- B4: scatter dh through the encoders ------------------------------------------------
-L4D_HD float l4d_dfeat(const DevModel& M, const BwSample& s, int row) {
-  return l4d_dot64(s.dh, M.sig_w1t + (size_t)row * L4D_H);
-}
+// where dL/dfeature comes from: recomputed on demand from dh (single-kernel path) or read from the
+// SoA plane the dense backward kernel wrote (split pipeline)
+struct DfeatFromDh {
+  const DevModel* M;
+  const BwSample* s;
+  L4D_HD float operator()(int row) const { return l4d_dot64(s->dh, M->sig_w1t + (size_t)row * L4D_H); }
+};
+struct DfeatFromPlane {
+  const float* base;     // dfeat + p
+  size_t stride;         // P
+  L4D_HD float operator()(int row) const { return l4d_ld1(base + (size_t)row * stride); }
+};
+
+// scatter dL/dfeature through the encoders of one sample at (x,y,z) with its flow; dflow[6] out
+template <class DF>
+L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
+                             const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6]);
 
 L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads& G, BwSample& s) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) s.dflow[k] = 0.f;
   if (!s.active) return;
+  DfeatFromDh df{&M, &s};
+  l4d_bw_scatter_t(M, F, G, s.x, s.y, s.z, s.flow, df, s.dflow);
+}
+
+template <class DF>
+L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
+                             const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6]) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dflow[k] = 0.f;
   const int nS = (int)M.n_scales;
   const int L = (int)M.gs.n_levels;
   const int row_plane_d = nS * 8;
@@ -187,9 +205,8 @@ L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads&
   const int row_hash_d = row_hash_s + L * 4;
   float wc, wf, wb;
   l4d_agg_weights(F, wc, wf, wb);
-  const float x = s.x, y = s.y, z = s.z;
-  const float xf0 = x + s.flow[0], xf1 = y + s.flow[1], xf2 = z + s.flow[2];
-  const float xw0 = x + s.flow[3], xw1 = y + s.flow[4], xw2 = z + s.flow[5];
+  const float xf0 = x + flow[0], xf1 = y + flow[1], xf2 = z + flow[2];
+  const float xw0 = x + flow[3], xw1 = y + flow[4], xw2 = z + flow[5];
 
 #pragma unroll 1
   for (int sc = 0; sc < nS; ++sc) {
@@ -198,7 +215,7 @@ L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads&
     {   // static planes: product rule over (x,y) (x,z) (y,z)
       float d[8], v0[8], v1[8], v2[8], dummy[8], g[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) d[c] = l4d_dfeat(M, s, sc * 8 + c);
+      for (int c = 0; c < 8; ++c) d[c] = l4d_dfeat_fn(sc * 8 + c);
       Bilerp b0 = l4d_bilerp(x, R, y, R), b1 = l4d_bilerp(x, R, z, R), b2 = l4d_bilerp(y, R, z, R);
       l4d_plane_sample<false>(M.planes[sc][0], R, b0, v0, dummy);
       l4d_plane_sample<false>(M.planes[sc][1], R, b1, v1, dummy);
@@ -216,7 +233,7 @@ L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads&
     {   // time planes (x,t) (y,t) (z,t): three queries, warped ones also feed d(coords) -> flow
       float d[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) d[c] = l4d_dfeat(M, s, row_plane_d + sc * 8 + c);
+      for (int c = 0; c < 8; ++c) d[c] = l4d_dfeat_fn(row_plane_d + sc * 8 + c);
 #pragma unroll 1
       for (int qi = 0; qi < 3; ++qi) {
         const float wq = qi == 0 ? wc : (qi == 1 ? wf : wb);
@@ -240,8 +257,8 @@ L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads&
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v0[c] * v1[c]; c2 = fmaf(g[c], x2[c], c2); }
         l4d_plane_scatter(G.planes_cl[sc][5], R, b2, g);
-        if (qi == 1) { s.dflow[0] += c0; s.dflow[1] += c1; s.dflow[2] += c2; }
-        if (qi == 2) { s.dflow[3] += c0; s.dflow[4] += c1; s.dflow[5] += c2; }
+        if (qi == 1) { dflow[0] += c0; dflow[1] += c1; dflow[2] += c2; }
+        if (qi == 2) { dflow[3] += c0; dflow[4] += c1; dflow[5] += c2; }
       }
     }
   }
@@ -251,8 +268,8 @@ L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads&
   for (int l = 0; l < L; ++l) {
     uint32_t idx[8]; float w[8];
     l4d_corners3(M.gs, l, x, y, z, idx, w);
-    const float d0 = l4d_dfeat(M, s, row_hash_s + 4 * l + 0), d1 = l4d_dfeat(M, s, row_hash_s + 4 * l + 1);
-    const float d2 = l4d_dfeat(M, s, row_hash_s + 4 * l + 2), d3 = l4d_dfeat(M, s, row_hash_s + 4 * l + 3);
+    const float d0 = l4d_dfeat_fn(row_hash_s + 4 * l + 0), d1 = l4d_dfeat_fn(row_hash_s + 4 * l + 1);
+    const float d2 = l4d_dfeat_fn(row_hash_s + 4 * l + 2), d3 = l4d_dfeat_fn(row_hash_s + 4 * l + 3);
     float* base = G.hs + (size_t)M.gs.offset[l] * 4;
 #pragma unroll
     for (int c = 0; c < 8; ++c) l4d_red4(base + (size_t)idx[c] * 4, w[c] * d0, w[c] * d1, w[c] * d2, w[c] * d3);
@@ -268,7 +285,7 @@ L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads&
     for (int l = 0; l < L; ++l) {
       uint32_t idx[4]; float w[4];
       l4d_corners2(M.gd[p], l, ca, cb, idx, w);
-      const float d = wc * l4d_dfeat(M, s, row_hash_d + p * L + l);
+      const float d = wc * l4d_dfeat_fn(row_hash_d + p * L + l);
       const float e0 = d * F.cur.basis[0], e1 = d * F.cur.basis[1], e2 = d * F.cur.basis[2], e3 = d * F.cur.basis[3];
       const float slo = F.cur.single ? 1.0f : F.cur.w_lo;
       const size_t off = (size_t)M.gd[p].offset[l] * 4;

@@ -91,7 +91,10 @@ struct SavedView {
   float* flow_in;   // [16][P]
   float* sigma;     // [P]
   float* attr;      // [2][P]
-  float* hidden;    // [64][P]  scratch used inside the backward kernel only
+  float* hidden;    // [ctas][64][NT] per-CTA scratch of the dense backward kernel
+  float* flow;      // [6][P]   flow-field output (split pipeline: the scatter kernel needs the warped positions)
+  float* dfeat;     // [sigma_in_dim][P]  dL/dfeature, dense backward -> scatter kernel
+  float* dflow;     // [6][P]   dL/dflow, scatter kernel -> flow backward kernel
   size_t P;
 };
 
@@ -544,6 +547,10 @@ struct FeatSink {
   float* dense;     // optional dense [sigma_in_dim] row (debug entry point) or nullptr
 };
 
+// push n feature values (held in the exchange column xb[0..n)) to the sinks and, when ACC, into the
+// first sigma layer.  The split pipeline (k_fwd_gather) runs with ACC=false: no MLP registers live
+// across the gathers.
+template <bool ACC>
 L4D_HD void l4d_emit(float (&acc)[L4D_H], const DevModel& M, float* xb, int xs, int row0, int n,
                      const FeatSink& sink) {
   if (sink.feat) {
@@ -552,7 +559,7 @@ L4D_HD void l4d_emit(float (&acc)[L4D_H], const DevModel& M, float* xb, int xs, 
   if (sink.dense) {
     for (int i = 0; i < n; ++i) sink.dense[row0 + i] = xb[i * xs];
   }
-  l4d_layer64(acc, xb, xs, n, M.sig_w1t + (size_t)row0 * L4D_H);
+  if (ACC) l4d_layer64(acc, xb, xs, n, M.sig_w1t + (size_t)row0 * L4D_H);
 }
 
 // weights of the neighbour aggregation 0.5*cur + 0.25*(fwd+bwd) with the
@@ -563,9 +570,10 @@ L4D_HD void l4d_agg_weights(const L4DFrame& F, float& wc, float& wf, float& wb) 
   wc = 0.5f + (F.has_fwd ? 0.f : 0.25f) + (F.has_bwd ? 0.f : 0.25f);
 }
 
-L4D_HD void l4d_density_sample(const DevModel& M, const L4DFrame& F, float x, float y, float z,
-                               float* xb, int xs, const FeatSink& sink, float* flow_in_save, size_t fi_stride,
-                               float& sigma, float& h0_raw, float geo[L4D_GEO], float flow_out[6]) {
+// all encoder features of one sample given its flow; order = cat([plane_s, plane_d, hash_s, hash_d])
+template <bool ACC>
+L4D_HD void l4d_gather_features(const DevModel& M, const L4DFrame& F, float x, float y, float z, const float (&flow)[8],
+                                float* xb, int xs, const FeatSink& sink, float (&acc)[L4D_H]) {
   const int nS = (int)M.n_scales;
   const int L = (int)M.gs.n_levels;
   const int row_plane_d = nS * 8;
@@ -573,22 +581,8 @@ L4D_HD void l4d_density_sample(const DevModel& M, const L4DFrame& F, float x, fl
   const int row_hash_d = row_hash_s + L * 4;
   float wc, wf, wb;
   l4d_agg_weights(F, wc, wf, wb);
-
-  // ---- flow (needed first: the warped queries depend on it) ----
-  float flow[8];
-  {
-    l4d_flow_inputs(M, F.flow_basis, x, y, z, xb, xs, flow_in_save, fi_stride);
-    uint32_t a, b, c, d;
-    l4d_flow_mlp(M, xb, xs, flow, a, b, c, d);
-  }
-#pragma unroll
-  for (int k = 0; k < 6; ++k) flow_out[k] = flow[k];
   const float xf0 = x + flow[0], xf1 = y + flow[1], xf2 = z + flow[2];     // lidar4d.py:158
   const float xw0 = x + flow[3], xw1 = y + flow[4], xw2 = z + flow[5];     // lidar4d.py:167
-
-  float acc[L4D_H];
-#pragma unroll
-  for (int k = 0; k < L4D_H; ++k) acc[k] = 0.f;
 
   // ---- hex-planes (planes_field.py:87-141) ----
 #pragma unroll 1
@@ -604,7 +598,7 @@ L4D_HD void l4d_density_sample(const DevModel& M, const L4DFrame& F, float x, fl
       l4d_plane_sample<false>(M.planes[s][3], R, b2, v2, dummy);
 #pragma unroll
       for (int c = 0; c < 8; ++c) xb[c * xs] = (v0[c] * v1[c]) * v2[c];
-      l4d_emit(acc, M, xb, xs, s * 8, 8, sink);
+      l4d_emit<ACC>(acc, M, xb, xs, s * 8, 8, sink);
     }
     // dynamic: planes 2 (x,t), 4 (y,t), 5 (z,t); three queries
     {
@@ -629,7 +623,7 @@ L4D_HD void l4d_density_sample(const DevModel& M, const L4DFrame& F, float x, fl
       }
 #pragma unroll
       for (int c = 0; c < 8; ++c) xb[c * xs] = comb[c];
-      l4d_emit(acc, M, xb, xs, row_plane_d + s * 8, 8, sink);
+      l4d_emit<ACC>(acc, M, xb, xs, row_plane_d + s * 8, 8, sink);
     }
   }
 
@@ -640,7 +634,7 @@ L4D_HD void l4d_density_sample(const DevModel& M, const L4DFrame& F, float x, fl
     l4d_encode3_f4(M.gs, M.hs, l, x, y, z, f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) xb[i * xs] = f[i];
-    l4d_emit(acc, M, xb, xs, row_hash_s + l * 4, 4, sink);
+    l4d_emit<ACC>(acc, M, xb, xs, row_hash_s + l * 4, 4, sink);
   }
 
   // ---- dynamic hash: planes xy, xz, yz at (x,t), (x+f+,t+), (x+f-,t-) (hash_field.py:146-158) ----
@@ -656,14 +650,13 @@ L4D_HD void l4d_density_sample(const DevModel& M, const L4DFrame& F, float x, fl
       if (wb != 0.f) v = fmaf(wb, l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], F.bwd, l, ba, bb), v);
       xb[l * xs] = v;
     }
-    l4d_emit(acc, M, xb, xs, row_hash_d + p * L, L, sink);
+    l4d_emit<ACC>(acc, M, xb, xs, row_hash_d + p * L, L, sink);
   }
+}
 
-  // ---- tcnn pads the MLP input to a multiple of 16 with ones [tcnn-ext] ----
-  for (int k = (int)M.sigma_in_dim; k < (int)M.sigma_in_pad; ++k) l4d_axpy64(acc, 1.0f, M.sig_w1t + (size_t)k * L4D_H);
-
-  // ---- sigma MLP second layer + trunc_exp (lidar4d.py:181-183) ----
-  uint32_t m0, m1;
+// second sigma layer + trunc_exp from the hidden pre-activations (lidar4d.py:181-183)
+L4D_HD void l4d_sigma_head(const DevModel& M, float (&acc)[L4D_H], float* xb, int xs, uint32_t& m0, uint32_t& m1,
+                           float& sigma, float& h0_raw, float geo[L4D_GEO]) {
   l4d_relu_store(acc, xb, xs, m0, m1);
   float out[16];
 #pragma unroll
@@ -673,6 +666,40 @@ L4D_HD void l4d_density_sample(const DevModel& M, const L4DFrame& F, float x, fl
   sigma = expf(out[0]);
 #pragma unroll
   for (int k = 0; k < L4D_GEO; ++k) geo[k] = out[1 + k];
+}
+
+// fused density of one sample (used by the single-kernel path and the debug entry point)
+L4D_HD void l4d_density_sample(const DevModel& M, const L4DFrame& F, float x, float y, float z,
+                               float* xb, int xs, const FeatSink& sink, float* flow_in_save, size_t fi_stride,
+                               float& sigma, float& h0_raw, float geo[L4D_GEO], float flow_out[6]) {
+  // ---- flow (needed first: the warped queries depend on it) ----
+  float flow[8];
+  {
+    l4d_flow_inputs(M, F.flow_basis, x, y, z, xb, xs, flow_in_save, fi_stride);
+    uint32_t a, b, c, d;
+    l4d_flow_mlp(M, xb, xs, flow, a, b, c, d);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) flow_out[k] = flow[k];
+  float acc[L4D_H];
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) acc[k] = 0.f;
+  l4d_gather_features<true>(M, F, x, y, z, flow, xb, xs, sink, acc);
+  // ---- tcnn pads the MLP input to a multiple of 16 with ones [tcnn-ext] ----
+  for (int k = (int)M.sigma_in_dim; k < (int)M.sigma_in_pad; ++k) l4d_axpy64(acc, 1.0f, M.sig_w1t + (size_t)k * L4D_H);
+  uint32_t m0, m1;
+  l4d_sigma_head(M, acc, xb, xs, m0, m1, sigma, h0_raw, geo);
+}
+
+// first sigma layer from features stored as SoA planes (split pipeline / backward recompute)
+L4D_HD void l4d_sigma_hidden_from_feats(const DevModel& M, const float* feat, size_t stride, bool active,
+                                        float (&acc)[L4D_H]) {
+#pragma unroll
+  for (int k = 0; k < L4D_H; ++k) acc[k] = 0.f;
+  if (active) {
+    for (int k = 0; k < (int)M.sigma_in_dim; ++k) l4d_axpy64(acc, feat[(size_t)k * stride], M.sig_w1t + (size_t)k * L4D_H);
+    for (int k = (int)M.sigma_in_dim; k < (int)M.sigma_in_pad; ++k) l4d_axpy64(acc, 1.0f, M.sig_w1t + (size_t)k * L4D_H);
+  }
 }
 
 // ---------------------------------------------------------------------------

@@ -176,7 +176,7 @@ static inline void build_grads(const L4DConfig* c, const L4DMasterGrads* g, void
 
 #define L4D_NT 128
 #define L4D_BWD_SCRATCH_CTAS 1024
-struct SavedLayout { size_t feat, flow_in, sigma, attr, hidden, total; };
+struct SavedLayout { size_t feat, flow_in, sigma, attr, hidden, flow, dfeat, dflow, total; };
 static inline SavedLayout saved_layout(const L4DConfig* c, uint32_t n_rays, uint32_t S) {
   SavedLayout L;
   const size_t P = (size_t)n_rays * S;
@@ -187,6 +187,9 @@ static inline SavedLayout saved_layout(const L4DConfig* c, uint32_t n_rays, uint
   L.sigma = take(P * sizeof(float));
   L.attr = take(P * 2 * sizeof(float));
   L.hidden = take((size_t)L4D_BWD_SCRATCH_CTAS * 64 * L4D_NT * sizeof(float));
+  L.flow = take(P * 6 * sizeof(float));
+  L.dfeat = take(P * c->sigma_in_dim * sizeof(float));
+  L.dflow = take(P * 6 * sizeof(float));
   L.total = o;
   return L;
 }
@@ -199,6 +202,9 @@ static inline SavedView saved_view(const L4DConfig* c, void* saved, uint32_t n_r
   v.sigma = reinterpret_cast<float*>(b + L.sigma);
   v.attr = reinterpret_cast<float*>(b + L.attr);
   v.hidden = reinterpret_cast<float*>(b + L.hidden);
+  v.flow = reinterpret_cast<float*>(b + L.flow);
+  v.dfeat = reinterpret_cast<float*>(b + L.dfeat);
+  v.dflow = reinterpret_cast<float*>(b + L.dflow);
   v.P = (size_t)n_rays * S;
   return v;
 }

@@ -306,6 +306,8 @@ __device__ __forceinline__ float tile_colsum(const float* __restrict__ T) {
   return s;
 }
 
+#include "l4d_split.cuh"
+
 // =============================================================================
 // forward render kernel
 // =============================================================================
@@ -740,6 +742,19 @@ static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid) {
   return L4D_OK;
 }
 
+static void fill_split(SplitArgs& A, const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
+                       void* saved) {
+  memset(&A, 0, sizeof(A));
+  build_model(cfg, staged, A.M);
+  A.F = *frame;
+  A.rays_o = rays->rays_o; A.rays_d = rays->rays_d;
+  A.n_rays = rays->n_rays; A.S = rays->n_steps; A.perturb = rays->perturb;
+  A.seed = rays->seed; A.ray_offset = rays->ray_offset;
+  A.sv = saved_view(cfg, saved, rays->n_rays, rays->n_steps);
+}
+
+#define L4D_FLAG_FUSED 1u   /* L4DRays.reserved bit 0: single-kernel path */
+
 extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
                                   float* depth, float* image, float* wsum, float* weights, float* zvals, void* saved,
                                   size_t saved_bytes, void* stream) {
@@ -749,24 +764,47 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
   if (rc != L4D_OK) return rc;
   if (!staged || !frame || !depth || !image || !wsum) return l4d_fail(L4D_EINVAL, "null pointer");
   if (rays->n_rays == 0) return L4D_OK;
-  FwdArgs A;
-  memset(&A, 0, sizeof(A));
-  build_model(cfg, staged, A.M);
-  A.F = *frame;
-  A.rays_o = rays->rays_o; A.rays_d = rays->rays_d;
-  A.n_rays = rays->n_rays; A.S = rays->n_steps; A.perturb = rays->perturb;
-  A.seed = rays->seed; A.ray_offset = rays->ray_offset;
-  A.depth = depth; A.image = image; A.wsum = wsum; A.weights = weights; A.zvals = zvals;
-  A.train = saved ? 1u : 0u;
-  if (saved) {
-    if (saved_bytes < saved_layout(cfg, rays->n_rays, rays->n_steps).total) return l4d_fail(L4D_ESIZE, "saved buffer too small");
-    A.sv = saved_view(cfg, saved, rays->n_rays, rays->n_steps);
+  if (saved && saved_bytes < saved_layout(cfg, rays->n_rays, rays->n_steps).total) return l4d_fail(L4D_ESIZE, "saved buffer too small");
+  const bool fused = (rays->reserved & L4D_FLAG_FUSED) || !saved;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fused) {
+    FwdArgs A;
+    memset(&A, 0, sizeof(A));
+    build_model(cfg, staged, A.M);
+    A.F = *frame;
+    A.rays_o = rays->rays_o; A.rays_d = rays->rays_d;
+    A.n_rays = rays->n_rays; A.S = rays->n_steps; A.perturb = rays->perturb;
+    A.seed = rays->seed; A.ray_offset = rays->ray_offset;
+    A.depth = depth; A.image = image; A.wsum = wsum; A.weights = weights; A.zvals = zvals;
+    A.train = saved ? 1u : 0u;
+    if (saved) A.sv = saved_view(cfg, saved, rays->n_rays, rays->n_steps);
+    const size_t smem = (64 * L4D_NT + 80 + 128 + 32) * sizeof(float);
+    int grid;
+    rc = grid_for(k_render_fwd<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
+    if (rc != L4D_OK) return rc;
+    k_render_fwd<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+    L4D_CUDA(cudaGetLastError());
+    return L4D_OK;
   }
-  const size_t smem = (64 * L4D_NT + 80 + 128 + 32) * sizeof(float);
-  int grid;
-  rc = grid_for(k_render_fwd<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
-  if (rc != L4D_OK) return rc;
-  k_render_fwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  SplitArgs A;
+  fill_split(A, cfg, staged, frame, rays, saved);
+  A.depth = depth; A.image = image; A.wsum = wsum; A.weights = weights; A.zvals = zvals;
+  A.train = 1u;
+  const size_t P = (size_t)rays->n_rays * rays->n_steps;
+  {
+    const size_t smem = 64 * L4D_NT * sizeof(float);
+    int grid;
+    rc = grid_for(k_fwd_gather<L4D_NT>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
+    if (rc != L4D_OK) return rc;
+    k_fwd_gather<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+  }
+  {
+    const size_t smem = (64 * L4D_NT + 80 + 128 + 32) * sizeof(float);
+    int grid;
+    rc = grid_for(k_fwd_dense<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
+    if (rc != L4D_OK) return rc;
+    k_fwd_dense<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+  }
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -787,6 +825,39 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
     for (uint32_t s = 0; s < cfg->time_resolution; ++s)
       if (!grads->hash_dynamic[p][s]) return l4d_fail(L4D_EINVAL, "null hash_dynamic gradient buffer");
   if (rays->n_rays == 0) return L4D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(rays->reserved & L4D_FLAG_FUSED)) {
+    SplitArgs A;
+    fill_split(A, cfg, staged, frame, rays, const_cast<void*>(saved));
+    build_grads(cfg, grads, grad_work, A.G);
+    A.g_depth = g_depth; A.g_image = g_image; A.g_wsum = g_wsum; A.g_weights = g_weights;
+    A.train = 1u;
+    const size_t P = (size_t)rays->n_rays * rays->n_steps;
+    const uint32_t tiles = (uint32_t)((P + L4D_NT - 1) / L4D_NT);
+    {
+      const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD + 80 + 128 + 128 + 32 + L4D_MAX_TILES) * sizeof(float);
+      int grid;
+      rc = grid_for(k_bwd_dense<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
+      if (rc != L4D_OK) return rc;
+      if (grid > L4D_BWD_SCRATCH_CTAS) grid = L4D_BWD_SCRATCH_CTAS;
+      k_bwd_dense<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+    }
+    {
+      int grid;
+      rc = grid_for(k_bwd_scatter<L4D_NT>, L4D_NT, 0, tiles, grid);
+      if (rc != L4D_OK) return rc;
+      k_bwd_scatter<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
+    }
+    if (frame->has_fwd || frame->has_bwd) {     // with no neighbour frame nothing reaches the flow field
+      const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD) * sizeof(float);
+      int grid;
+      rc = grid_for(k_bwd_flow<L4D_NT>, L4D_NT, smem, tiles, grid);
+      if (rc != L4D_OK) return rc;
+      k_bwd_flow<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+    }
+    L4D_CUDA(cudaGetLastError());
+    return L4D_OK;
+  }
   BwdArgs A;
   memset(&A, 0, sizeof(A));
   build_model(cfg, staged, A.M);
@@ -802,7 +873,7 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
   rc = grid_for(k_render_bwd<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
   if (rc != L4D_OK) return rc;
   if (grid > L4D_BWD_SCRATCH_CTAS) grid = L4D_BWD_SCRATCH_CTAS;
-  k_render_bwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  k_render_bwd<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }

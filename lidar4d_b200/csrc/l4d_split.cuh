@@ -1,0 +1,336 @@
+// l4d_split.cuh - the split pipeline (default path).
+//
+// Why: the single-kernel path (k_render_fwd / k_render_bwd in l4d_kernels.cu) keeps 64-wide MLP
+// accumulators live across the irregular gathers / scatters -> 255 registers, 8 warps/SM, and ncu
+// shows both kernels latency-bound on long_scoreboard with DRAM at 2% (profiles/r01_v1_*).  Here
+// the memory-irregular work runs in lean, high-occupancy kernels (thread == sample, grid-stride,
+// no shared memory) and the dense work (MLPs, compositing) in per-ray kernels; they exchange
+// ~1 KB/sample through SoA planes [k][P] (every warp access = one 128 B line), which the idle HBM
+// absorbs.  Same per-sample functions (l4d_core.cuh / l4d_bwd.cuh), same numerics.
+//
+//   forward :  k_fwd_gather  ->  k_fwd_dense
+//   backward:  k_bwd_dense   ->  k_bwd_scatter  ->  k_bwd_flow
+#pragma once
+#include "l4d_bwd.cuh"
+#include "l4d_core.cuh"
+
+struct SplitArgs {
+  DevModel M;
+  L4DFrame F;
+  DevGrads G;
+  const float* rays_o;
+  const float* rays_d;
+  uint32_t n_rays, S, perturb, train;
+  uint64_t seed, ray_offset;
+  float *depth, *image, *wsum, *weights, *zvals;
+  const float *g_depth, *g_image, *g_wsum, *g_weights;
+  SavedView sv;
+};
+
+// -------------------------------------------------------------------------------------------
+// forward 1/2: encoders.  thread == sample; writes features, flow-MLP inputs and flow.
+// -------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 4) k_fwd_gather(const __grid_constant__ SplitArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xb = smem + threadIdx.x;          // exchange column for the flow MLP, stride NT
+  const DevModel& M = A.M;
+  const size_t P = A.sv.P;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  for (size_t base = (size_t)blockIdx.x * NT; base < P; base += (size_t)gridDim.x * NT) {
+    const size_t p = base + threadIdx.x;
+    if (p >= P) continue;
+    const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
+    const float zj = l4d_z(rs, A.ray_offset + ray, j);
+    const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
+    const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
+    const float z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
+    float flow[8];
+    {
+      l4d_flow_inputs(M, A.F.flow_basis, x, y, z, xb, NT, A.sv.flow_in + p, P);
+      uint32_t a, b, c, d;
+      l4d_flow_mlp(M, xb, NT, flow, a, b, c, d);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) A.sv.flow[(size_t)k * P + p] = flow[k];
+    FeatSink sink;
+    sink.feat = A.sv.feat; sink.P = P; sink.p = p; sink.dense = nullptr;
+    float dummy[L4D_H];
+    l4d_gather_features<false>(M, A.F, x, y, z, flow, xb, NT, sink, dummy);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// forward 2/2: sigma MLP, compositing, attribute heads.  One CTA per ray, tiles of NT samples.
+// -------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k_fwd_dense(const __grid_constant__ SplitArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xbuf = smem;
+  float* s_enc = xbuf + 64 * NT;
+  float* s_cdir = s_enc + 80;
+  float* s_w = s_cdir + 128;
+  const DevModel& M = A.M;
+  const int tid = threadIdx.x;
+  float* xb = xbuf + tid;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  const uint32_t S = A.S;
+  for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
+    const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
+    __syncthreads();
+    for (int i = tid; i < L4D_ENC; i += NT) {
+      const int dim = i / 24, k = (i % 24) >> 1, ph = i & 1;
+      s_enc[i] = l4d_freq(dim == 0 ? dx : (dim == 1 ? dy : dz), k, ph);
+    }
+    __syncthreads();
+    for (int i = tid; i < 128; i += NT) s_cdir[i] = l4d_attr_cdir(M, i >> 6, i & 63, s_enc);
+    __syncthreads();
+    float carry = 1.f, pd = 0.f, p0 = 0.f, p1 = 0.f, pw = 0.f;
+    const uint64_t rg = A.ray_offset + ray;
+    for (uint32_t j0 = 0; j0 < S; j0 += NT) {
+      const uint32_t j = j0 + tid;
+      const bool valid = j < S;
+      const size_t p = (size_t)ray * S + (valid ? j : 0);
+      float zj = 0.f, alpha = 0.f, sigma = 0.f, h0, geo[L4D_GEO];
+      {
+        float acc[L4D_H];
+        l4d_sigma_hidden_from_feats(M, A.sv.feat + p, A.sv.P, valid, acc);
+        uint32_t m0, m1;
+        l4d_sigma_head(M, acc, xb, NT, m0, m1, sigma, h0, geo);
+      }
+      if (valid) {
+        zj = l4d_z(rs, rg, j);
+        const float delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
+        alpha = l4d_alpha(M, delta, sigma);
+      }
+      const float v = valid ? (1.0f - alpha) + 1e-15f : 1.f;
+      float total;
+      const float T = carry * block_excl_prod<NT>(v, s_w, total);
+      carry *= total;
+      const float w = alpha * T;
+      float a0 = 0.f, a1 = 0.f;
+      if (valid && w > 1e-4f) {
+        a0 = l4d_attr_net(M, 0, s_cdir, geo, xb, NT);
+        a1 = l4d_attr_net(M, 1, s_cdir, geo, xb, NT);
+      }
+      pd = fmaf(w, zj, pd); p0 = fmaf(w, a0, p0); p1 = fmaf(w, a1, p1); pw += w;
+      if (valid) {
+        if (A.train) { A.sv.sigma[p] = sigma; A.sv.attr[p] = a0; A.sv.attr[A.sv.P + p] = a1; }
+        if (A.weights) A.weights[p] = w;
+        if (A.zvals) A.zvals[p] = zj;
+      }
+    }
+    pd = block_sum<NT>(pd, s_w); p0 = block_sum<NT>(p0, s_w); p1 = block_sum<NT>(p1, s_w); pw = block_sum<NT>(pw, s_w);
+    if (tid == 0) { A.depth[ray] = pd; A.image[2 * ray] = p0; A.image[2 * ray + 1] = p1; A.wsum[ray] = pw; }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// backward 1/3: compositing + attribute heads + sigma MLP, weight gradients; writes dL/dfeature.
+// -------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k_bwd_dense(const __grid_constant__ SplitArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xbuf = smem;
+  float* TA = xbuf + 64 * NT;
+  float* TB = TA + NT * L4D_TILE_LD;
+  float* s_enc = TB + NT * L4D_TILE_LD;
+  float* s_cdir = s_enc + 80;
+  float* s_csum = s_cdir + 128;
+  float* s_w = s_csum + 128;
+  float* s_tstart = s_w + 32;
+  const DevModel& M = A.M;
+  const DevGrads& G = A.G;
+  const int tid = threadIdx.x;
+  float* xb = xbuf + tid;
+  float* ta_row = TA + (size_t)tid * L4D_TILE_LD;
+  float* tb_row = TB + (size_t)tid * L4D_TILE_LD;
+  float* hid = A.sv.hidden + (size_t)blockIdx.x * 64 * NT + tid;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  const uint32_t S = A.S;
+  const int n_tiles = (int)((S + NT - 1) / NT);
+  const float kk = M.active_sensor ? 2.0f : 1.0f;
+  const int n_chunks = (int)(M.sigma_in_pad + 63) / 64;
+
+  for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
+    const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
+    const float gd = __ldg(A.g_depth + ray), gi0 = __ldg(A.g_image + 2 * ray), gi1 = __ldg(A.g_image + 2 * ray + 1);
+    const float gws = A.g_wsum ? __ldg(A.g_wsum + ray) : 0.f;
+    const uint64_t rg = A.ray_offset + ray;
+    __syncthreads();
+    for (int i = tid; i < L4D_ENC; i += NT) {
+      const int dim = i / 24, k = (i % 24) >> 1, ph = i & 1;
+      s_enc[i] = l4d_freq(dim == 0 ? dx : (dim == 1 ? dy : dz), k, ph);
+    }
+    for (int i = tid; i < 128; i += NT) s_csum[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < 128; i += NT) s_cdir[i] = l4d_attr_cdir(M, i >> 6, i & 63, s_enc);
+    __syncthreads();
+    {   // pass 1: transmittance at the start of every tile
+      float carry = 1.f;
+      for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t j = (uint32_t)t * NT + tid;
+        float v = 1.f;
+        if (j < S) {
+          const float zj = l4d_z(rs, rg, j);
+          const float delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
+          v = (1.0f - l4d_alpha(M, delta, A.sv.sigma[(size_t)ray * S + j])) + 1e-15f;
+        }
+        if (tid == 0) s_tstart[t] = carry;
+        float total;
+        block_excl_prod<NT>(v, s_w, total);
+        carry *= total;
+      }
+    }
+    __syncthreads();
+    float suffix = 0.f;
+    for (int t = n_tiles - 1; t >= 0; --t) {
+      const uint32_t j = (uint32_t)t * NT + tid;
+      BwSample s;
+      s.active = j < S;
+      const size_t p = (size_t)ray * S + (s.active ? j : 0);
+      s.masked = false;
+      s.dsigma = 0.f; s.da[0] = 0.f; s.da[1] = 0.f;
+      float v = 1.f, alpha = 0.f, gw = 0.f, delta = 0.f;
+      if (s.active) {
+        const float zj = l4d_z(rs, rg, j);
+        delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
+        alpha = l4d_alpha(M, delta, A.sv.sigma[p]);
+        v = (1.0f - alpha) + 1e-15f;
+        gw = gd * zj + gi0 * A.sv.attr[p] + gi1 * A.sv.attr[A.sv.P + p] + gws;
+        if (A.g_weights) gw += __ldg(A.g_weights + p);
+      }
+      float total, qtot;
+      const float T = s_tstart[t] * block_excl_prod<NT>(v, s_w, total);
+      const float w = alpha * T;
+      const float suf = suffix + block_excl_suffix_sum<NT>(gw * w, s_w, qtot);
+      suffix += qtot;
+      if (s.active) {
+        s.dsigma = (gw * T - suf / v) * (kk * delta * M.density_scale) * (1.0f - alpha);
+        s.masked = w > 1e-4f;
+        if (s.masked) { s.da[0] = w * gi0; s.da[1] = w * gi1; }
+      }
+      l4d_bw_sigma_fwd(M, s, A.sv.feat + p, A.sv.P, xb, NT, hid, NT);
+#pragma unroll 1
+      for (int net = 0; net < 2; ++net) {
+        uint32_t m1a, m1b;
+        l4d_bw_attr_a(M, net, s, s_cdir, xb, NT, ta_row, tb_row, m1a, m1b);
+        __syncthreads();
+        {
+          const float cs = tile_colsum<NT>(TB);
+          if (tid < 64) atomicAdd(G.att_w3[net] + tid, cs);
+        }
+        __syncthreads();
+        l4d_bw_attr_b(xb, NT, tb_row);
+        __syncthreads();
+        tile_outer_accum<NT>(TA, TB, 64, G.att_w2t[net]);
+        __syncthreads();
+        l4d_bw_attr_c(M, net, s, xb, NT, ta_row, tb_row, m1a, m1b);
+        __syncthreads();
+        tile_outer_accum<NT>(TA, TB, 16, G.att_w1t[net] + (size_t)L4D_ENC * 64);
+        {
+          const float cs = tile_colsum<NT>(TB);
+          if (tid < 64) s_csum[net * 64 + tid] += cs;
+        }
+        __syncthreads();
+      }
+      l4d_bw_sigma_a(M, s, hid, NT, xb, NT, ta_row, tb_row);
+      __syncthreads();
+      tile_outer_accum<NT>(TA, TB, 16, G.sig_w2);
+      __syncthreads();
+      l4d_bw_sigma_b(M, s, xb, NT, tb_row);
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        l4d_bw_sigma_c(M, s, A.sv.feat + p, A.sv.P, c, ta_row);
+        __syncthreads();
+        const int rows = min(64, (int)M.sigma_in_pad - c * 64);
+        tile_outer_accum<NT>(TA, TB, rows, G.sig_w1t + (size_t)c * 64 * 64);
+        __syncthreads();
+      }
+      // dL/dfeature for the scatter kernel
+      if (s.active) {
+        for (int k = 0; k < (int)M.sigma_in_dim; ++k)
+          A.sv.dfeat[(size_t)k * A.sv.P + p] = l4d_dot64(s.dh, M.sig_w1t + (size_t)k * L4D_H);
+      }
+    }
+    for (int i = tid; i < 2 * (L4D_ENC + 9) * 64; i += NT) {
+      const int net = i / ((L4D_ENC + 9) * 64);
+      const int r = (i / 64) % (L4D_ENC + 9), jx = i & 63;
+      const float cs = s_csum[net * 64 + jx];
+      if (r < L4D_ENC) atomicAdd(G.att_w1t[net] + (size_t)r * 64 + jx, s_enc[r] * cs);
+      else atomicAdd(G.att_w1t[net] + (size_t)(M.attr_in_dim + (r - L4D_ENC)) * 64 + jx, cs);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// backward 2/3: scatter dL/dfeature through the encoders (vector REDs), thread == sample.
+// -------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 4) k_bwd_scatter(const __grid_constant__ SplitArgs A) {
+  const DevModel& M = A.M;
+  const size_t P = A.sv.P;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  for (size_t p = (size_t)blockIdx.x * NT + threadIdx.x; p < P; p += (size_t)gridDim.x * NT) {
+    const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
+    const float zj = l4d_z(rs, A.ray_offset + ray, j);
+    const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
+    const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
+    const float z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
+    float flow[6], dflow[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) flow[k] = A.sv.flow[(size_t)k * P + p];
+    DfeatFromPlane df{A.sv.dfeat + p, P};
+    l4d_bw_scatter_t(M, A.F, A.G, x, y, z, flow, df, dflow);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) A.sv.dflow[(size_t)k * P + p] = dflow[k];
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// backward 3/3: flow MLP backprop + flow-grid scatter; tiles of NT consecutive samples.
+// -------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k_bwd_flow(const __grid_constant__ SplitArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xbuf = smem;
+  float* TA = xbuf + 64 * NT;
+  float* TB = TA + NT * L4D_TILE_LD;
+  float* xb = xbuf + threadIdx.x;
+  float* ta_row = TA + (size_t)threadIdx.x * L4D_TILE_LD;
+  float* tb_row = TB + (size_t)threadIdx.x * L4D_TILE_LD;
+  const DevModel& M = A.M;
+  const size_t P = A.sv.P;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  for (size_t base = (size_t)blockIdx.x * NT; base < P; base += (size_t)gridDim.x * NT) {
+    const size_t pp = base + threadIdx.x;
+    BwSample s;
+    s.active = pp < P;
+    s.masked = false;
+    s.x = s.y = s.z = 0.f;
+    const size_t p = s.active ? pp : 0;
+    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (s.active) {
+      const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
+      const float zj = l4d_z(rs, A.ray_offset + ray, j);
+      s.x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
+      s.y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
+      s.z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) g[k] = A.sv.dflow[(size_t)k * P + p];
+    }
+    __syncthreads();
+    l4d_bw_flow_fwd(M, s, A.sv.flow_in + p, P, xb, NT);
+    l4d_bw_flow_a(M, s, A.sv.flow_in + p, P, g, xb, NT, ta_row, tb_row);
+    __syncthreads();
+    tile_outer_accum<NT>(TA, TB, 8, A.G.flo_w2);
+    __syncthreads();
+    l4d_bw_flow_b(M, s, g, xb, NT, ta_row, tb_row);
+    __syncthreads();
+    tile_outer_accum<NT>(TA, TB, 64, A.G.flo_w1t);
+    __syncthreads();
+    l4d_bw_flow_c(M, A.F, A.G, s, A.sv.flow_in + p, P, xb, NT, ta_row, tb_row);
+    __syncthreads();
+    tile_outer_accum<NT>(TA, TB, 16, A.G.flo_w0t);
+  }
+}

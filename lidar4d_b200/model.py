@@ -213,8 +213,10 @@ class _RenderFn(torch.autograd.Function):
         rays.rays_o, rays.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
         rays.n_rays, rays.n_steps, rays.perturb = N, S, int(bool(perturb))
         rays.seed, rays.ray_offset = int(seed), int(ray_offset)
+        fused = eng.owner.pipeline == "fused"
+        rays.reserved = 1 if fused else 0
         saved, nsaved = None, 0
-        if train:
+        if train or not fused:          # the split pipeline exchanges features through this workspace
             nsaved = lib.l4d_saved_bytes(C.byref(eng.ccfg), N, S)
             saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
         ev = eng._events("fwd")
@@ -224,12 +226,13 @@ class _RenderFn(torch.autograd.Function):
                 C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(frame), C.byref(rays),
                 depth.data_ptr(), image.data_ptr(), wsum.data_ptr(),
                 weights.data_ptr() if want_weights else None, zvals.data_ptr() if want_weights else None,
-                saved.data_ptr() if train else None, nsaved, eng.stream())
+                saved.data_ptr() if saved is not None else None, nsaved, eng.stream())
             if ev: ev[1].record()
         _capi.check(lib, rc, "l4d_render_forward")
-        eng.n_launches += 1
+        eng.n_launches += 1 if fused else 2
         ctx.eng, ctx.frame, ctx.rays_args = eng, frame, (N, S, int(bool(perturb)), int(seed), int(ray_offset))
-        ctx.saved, ctx.nsaved = saved, nsaved
+        ctx.saved, ctx.nsaved = (saved, nsaved) if train else (None, 0)
+        ctx.fused = fused
         ctx.rays_o, ctx.rays_d = rays_o, rays_d
         ctx.staged = eng.staged
         ctx.want_weights = want_weights
@@ -258,6 +261,7 @@ class _RenderFn(torch.autograd.Function):
         rays = _capi.L4DRays()
         rays.rays_o, rays.rays_d = ctx.rays_o.data_ptr(), ctx.rays_d.data_ptr()
         rays.n_rays, rays.n_steps, rays.perturb, rays.seed, rays.ray_offset = N, S, perturb, seed, ray_offset
+        rays.reserved = 1 if ctx.fused else 0
         ev = eng._events("bwd")
         with torch.cuda.device(dev):
             if ev: ev[0].record()
@@ -271,7 +275,7 @@ class _RenderFn(torch.autograd.Function):
             _capi.check(lib, rc, "l4d_render_backward")
             rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), nwork, C.byref(tab), eng.stream())
             _capi.check(lib, rc, "l4d_unstage_grads")
-        eng.n_launches += 1 + 6 * eng.cfg.n_levels_plane + 11
+        eng.n_launches += (1 if ctx.fused else 3) + 6 * eng.cfg.n_levels_plane + 11
         eng.owner._last_grad_arena = flat
         ctx.saved = None
         return (None,) * 10 + tuple(views[n] for n in eng.names)
@@ -398,6 +402,9 @@ class LiDAR4D(LiDAR_Renderer):
         self.unet = unet if unet is not None else nn.Identity()
 
         self.materialize_weights = True    # return `weights` / `z_vals` like renderer.py:134-140
+        # "split": gather / dense / scatter kernels exchanging SoA planes (default, faster);
+        # "fused": the single-kernel forward and backward (csrc/l4d_kernels.cu)
+        self.pipeline = "split"
         self.jitter_seed = 0
         self._jitter_calls = 0
         self._last_grad_arena = None

@@ -58,12 +58,14 @@ CASES = [(0.4, 200, False, 3, False), (0.0, 150, True, 4, False), (1.0, 130, Tru
 MIN_RELU_MARGIN = 1e-8      # see tests/test_hostsim_parity.py
 
 
+@pytest.mark.parametrize("pipeline", ["split", "fused"])
 @pytest.mark.parametrize("t,S,perturb,seed,surface", CASES)
-def test_render_forward_backward(dev, t, S, perturb, seed, surface):
+def test_render_forward_backward(dev, t, S, perturb, seed, surface, pipeline):
     orc = O.build_seeded(small_config(), seed, flow_last_std=0.02)
     if surface:
         make_surface_like(orc)
     m = cuda_model_from_oracle(orc)
+    m.pipeline = pipeline
     m.jitter_seed = seed
     ro, rd = _rays(3, 8) if S < 700 else _rays(2, 5)
     N = ro.shape[0]
@@ -184,6 +186,11 @@ def test_full_size_properties(dev, full_model):
             assert torch.equal(a[k], b[k]), k
         c = m.render(ro_t, rd_t, tt, staged=True, max_ray_batch=64, num_steps=768, perturb=False)
         assert torch.equal(c["depth_lidar"], a["depth_lidar"]) and torch.equal(c["image_lidar"], a["image_lidar"])
+        # the single-kernel and the split pipeline run the same per-sample code: results agree to fp32 rounding
+        m.pipeline = "fused"
+        f = m.render(ro_t, rd_t, tt, num_steps=768, perturb=False)
+        m.pipeline = "split"
+        assert rel_err(f["depth_lidar"], a["depth_lidar"]) < 1e-5 and rel_err(f["image_lidar"], a["image_lidar"]) < 1e-5
     w = a["weights"]
     assert torch.isfinite(w).all() and float(w.min()) >= 0.0
     assert float(a["weights_sum_lidar"].max()) <= 1.0 + 1e-4
