@@ -84,6 +84,9 @@ typedef struct L4DConfig {
   float    near_lidar;
   float    far_lidar;
   float    density_scale;
+  uint32_t mlp_fp16;             /* 1: MLP weights are consumed as fp16-rounded working copies (as tcnn's half
+                                    params) and the dense kernels run on tcgen05 tensor cores; 0: fp32 FMA */
+  uint32_t reserved;
 } L4DConfig;
 
 /* One (.,tau) query of the time-sliced grids (model/hash_field.py:76-88). */

@@ -33,7 +33,7 @@ class L4DConfig(C.Structure):
                 ("sigma_in_dim", C.c_uint32), ("sigma_in_pad", C.c_uint32),
                 ("attr_in_dim", C.c_uint32), ("attr_in_pad", C.c_uint32),
                 ("bound", C.c_float), ("near_lidar", C.c_float), ("far_lidar", C.c_float),
-                ("density_scale", C.c_float)]
+                ("density_scale", C.c_float), ("mlp_fp16", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class L4DTimeQuery(C.Structure):
@@ -82,9 +82,10 @@ def _grid(g: GridGeometry) -> L4DGrid:
     return s
 
 
-def make_config(cfg: FieldConfig) -> L4DConfig:
+def make_config(cfg: FieldConfig, mlp_fp16: bool = False) -> L4DConfig:
     cfg.validate()
     c = L4DConfig()
+    c.mlp_fp16 = int(bool(mlp_fp16))
     c.hash_static = _grid(cfg.static_grid())
     for p in range(3):
         c.hash_dynamic[p] = _grid(cfg.dynamic_grid(p))

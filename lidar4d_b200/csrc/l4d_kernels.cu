@@ -85,6 +85,20 @@ __global__ void k_add(const float* __restrict__ src, float* __restrict__ dst, in
   if (i < n) dst[i] += src[i];
 }
 
+// round fp32 values to the nearest fp16-representable value (MLP weights in mlp_fp16 mode)
+__global__ void k_round_fp16(float* __restrict__ w, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w[i] = __half2float(__float2half_rn(w[i]));
+}
+// native W[n][k0 + k] (row stride ld) -> fp16 tcgen05 K-major interleaved layout [k/8][row_off + n][8], rows_total rows
+__global__ void k_pack_umma(const float* __restrict__ W, int ld, int n_rows, int k0, int K, __half* __restrict__ dst,
+                            int rows_total, int row_off) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * K) return;
+  int n = i / K, k = i % K;
+  dst[((size_t)(k >> 3) * rows_total + row_off + n) * 8 + (k & 7)] = __float2half_rn(__ldg(W + (size_t)n * ld + k0 + k));
+}
+
 static inline int nblk(size_t n, int t = 256) { return (int)((n + t - 1) / t); }
 
 extern "C" size_t l4d_staged_bytes(const L4DConfig* cfg) {
@@ -144,6 +158,19 @@ extern "C" int l4d_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, 
   k_copy_block<<<nblk(64 * 64), 256, 0, st>>>(m->flow_mlp[1], F(L.flo_w1), 64 * 64, 64 * 64);
   k_transpose<<<nblk(64 * 8), 256, 0, st>>>(m->flow_mlp[2], 64, F(L.flo_w2t), 64, 8, 64, 6);
   k_copy_block<<<nblk(8 * 64), 256, 0, st>>>(m->flow_mlp[2], F(L.flo_w2), 6 * 64, 8 * 64);
+  if (cfg->mlp_fp16) {
+    // every fp32 MLP working copy becomes fp16-representable (one rounding, shared by FMA and tensor-core paths)
+    const size_t lo = L.sig_w1t, hi = L.tc_sig_w1;
+    k_round_fp16<<<nblk((hi - lo) / 4), 256, 0, st>>>(F(lo), (int)((hi - lo) / 4));
+  }
+  // tensor-core operand copies
+  k_pack_umma<<<nblk((size_t)64 * ip), 256, 0, st>>>(m->sigma_net, ip, 64, 0, ip, H(L.tc_sig_w1), 64, 0);
+  k_pack_umma<<<nblk(16 * 64), 256, 0, st>>>(m->sigma_net + 64 * ip, 64, 16, 0, 64, H(L.tc_sig_w2), 16, 0);
+  cudaMemsetAsync(b + L.tc_att_w1g, 0, 16 * 128 * 2, st);
+  for (int n = 0; n < 2; ++n) {
+    k_pack_umma<<<nblk(64 * 15), 256, 0, st>>>(att[n], ap, 64, L4D_ENC, 15, H(L.tc_att_w1g), 128, n * 64);
+    k_pack_umma<<<nblk(64 * 64), 256, 0, st>>>(att[n] + 64 * ap, 64, 64, 0, 64, H(L.tc_att_w2[n]), 64, 0);
+  }
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -307,6 +334,7 @@ __device__ __forceinline__ float tile_colsum(const float* __restrict__ T) {
 }
 
 #include "l4d_split.cuh"
+#include "l4d_dense_tc.cuh"
 
 // =============================================================================
 // forward render kernel
@@ -798,7 +826,13 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
     if (rc != L4D_OK) return rc;
     k_fwd_gather<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
   }
-  {
+  if (cfg->mlp_fp16) {
+    const size_t smem = dense_fwd_smem(cfg->sigma_in_pad).total + 1024;
+    int grid;
+    rc = grid_for(k_fwd_dense_tc, 128, smem, rays->n_rays, grid);
+    if (rc != L4D_OK) return rc;
+    k_fwd_dense_tc<<<grid, 128, smem, st>>>(A);
+  } else {
     const size_t smem = (64 * L4D_NT + 80 + 128 + 32) * sizeof(float);
     int grid;
     rc = grid_for(k_fwd_dense<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);

@@ -112,13 +112,20 @@ class _Engine:
     def __init__(self, owner: "LiDAR4D"):
         self.owner = owner
         self.cfg = owner.cfg
-        self.ccfg = _capi.make_config(self.cfg)
+        self.mlp_fp16 = False
+        self.ccfg = _capi.make_config(self.cfg, False)
         self.names = _capi.param_names(self.cfg)
         self.lib = None
         self.staged = None
         self._stamp = None
         self.n_launches = 0        # kernels of this library launched so far (bench "gpu_launches")
         self.timing = None         # {'fwd': [(ev0, ev1)], 'bwd': [...]}: CUDA events around the fused kernels
+
+    def set_mlp_fp16(self, on: bool):
+        if bool(on) != self.mlp_fp16:
+            self.mlp_fp16 = bool(on)
+            self.ccfg = _capi.make_config(self.cfg, self.mlp_fp16)
+            self._stamp = None            # force re-staging
 
     def _lib(self):
         if self.lib is None:
@@ -409,6 +416,14 @@ class LiDAR4D(LiDAR_Renderer):
         self._jitter_calls = 0
         self._last_grad_arena = None
         self._engine = _Engine(self)
+
+    # ---- precision / pipeline switches ------------------------------------------------------
+    def set_mlp_fp16(self, on: bool = True):
+        """True: MLP weights are consumed as fp16-rounded working copies of the fp32 masters (exactly how
+        tiny-cuda-nn's FullyFusedMLP holds them) and the dense kernels of the split pipeline run on the
+        tcgen05 tensor cores with hi/lo-split fp16 activations (fp32-class accuracy).  False: fp32 weights, FMA."""
+        self._engine.set_mlp_fp16(on)
+        return self
 
     # ---- nn.Module plumbing -----------------------------------------------------------------
     def forward(self, x, d, t):

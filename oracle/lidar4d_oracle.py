@@ -140,11 +140,11 @@ def mlp_layers(params: torch.Tensor, n_in_pad: int, hidden: int, n_hidden_layers
 
 
 def fused_mlp(x: torch.Tensor, params: torch.Tensor, n_in: int, n_out: int, hidden: int,
-              n_hidden_layers: int) -> torch.Tensor:
+              n_hidden_layers: int, weight_dtype: str = "fp32") -> torch.Tensor:
     """tcnn FullyFusedMLP [tcnn-ext]: pad inputs with ones to x16, ReLU hidden,
     linear output padded to 16 and sliced.  fp32 math."""
     n_in_pad = (n_in + 15) // 16 * 16
-    mats = mlp_layers(params, n_in_pad, hidden, n_hidden_layers)
+    mats = mlp_layers(working_table(params, weight_dtype), n_in_pad, hidden, n_hidden_layers)
     if n_in_pad > n_in:
         x = torch.cat([x, torch.ones(x.shape[0], n_in_pad - n_in, dtype=x.dtype, device=x.device)], -1)
     h = x
@@ -213,6 +213,7 @@ class OracleLiDAR4D(nn.Module):
         c = self.cfg
         c.validate()
         self.table_dtype = table_dtype
+        self.mlp_dtype = "fp32"          # "fp16": MLP weights as fp16-rounded working copies (tcnn keeps half params)
         self.cd = torch.float32          # compute dtype; float64 = "truth" mode (see to_float64)
         self.g_static = c.static_grid()
         self.g_dynamic = [c.dynamic_grid(p) for p in range(3)]
@@ -357,9 +358,10 @@ class OracleLiDAR4D(nn.Module):
         e = hash_encode(x01, self.p("flow_net.grid_enc.params"), self.g_flow, self.table_dtype, self.cd)
         h = self.interp_t(e, c.flow_n_levels, c.flow_n_features, basis)
         self._dbg_flow_in = h
-        h = torch.relu(h @ self.p("flow_net.mlp.0.weight").t())
-        h = torch.relu(h @ self.p("flow_net.mlp.2.weight").t())
-        return h @ self.p("flow_net.mlp.4.weight").t()
+        W = lambda n: working_table(self.p(n), self.mlp_dtype)
+        h = torch.relu(h @ W("flow_net.mlp.0.weight").t())
+        h = torch.relu(h @ W("flow_net.mlp.2.weight").t())
+        return h @ W("flow_net.mlp.4.weight").t()
 
     # -- LiDAR4D.flow / density / attribute ------------------------------------
     def flow(self, x: torch.Tensor, t) -> Dict[str, torch.Tensor]:
@@ -400,7 +402,7 @@ class OracleLiDAR4D(nn.Module):
         plane_d = 0.5 * plane_d + 0.25 * (plane_1 + plane_2)
         hash_d = 0.5 * hash_d + 0.25 * (hash_1 + hash_2)
         feats = torch.cat([plane_s, plane_d, hash_s, hash_d], -1)
-        h = fused_mlp(feats, self.p("sigma_net.params"), c.sigma_in_dim, 1 + c.geo_feat_dim, 64, 1)
+        h = fused_mlp(feats, self.p("sigma_net.params"), c.sigma_in_dim, 1 + c.geo_feat_dim, 64, 1, self.mlp_dtype)
         sigma = trunc_exp(h[:, 0])
         geo = h[:, 1:]
         out = {"sigma": sigma, "geo_feat": geo}
@@ -419,8 +421,8 @@ class OracleLiDAR4D(nn.Module):
             d, geo = d[mask], geo[mask]
         enc = frequency_encode((d.float() + 1) / 2, c.view_degree).to(self.cd)
         inp = torch.cat([enc, geo], -1)
-        inten = torch.sigmoid(fused_mlp(inp, self.p("intensity_net.params"), c.attr_in_dim, 1, 64, 2))
-        drop = torch.sigmoid(fused_mlp(inp, self.p("raydrop_net.params"), c.attr_in_dim, 1, 64, 2))
+        inten = torch.sigmoid(fused_mlp(inp, self.p("intensity_net.params"), c.attr_in_dim, 1, 64, 2, self.mlp_dtype))
+        drop = torch.sigmoid(fused_mlp(inp, self.p("raydrop_net.params"), c.attr_in_dim, 1, 64, 2, self.mlp_dtype))
         h = torch.cat([drop, inten], -1)
         if mask is not None:
             out[mask] = h

@@ -21,8 +21,9 @@ for L in levels:
     for N in sizes:
         sel = np.linspace(0, 65535, N).astype(np.int64)
         ro_t, rd_t = torch.from_numpy(ro[sel])[None].to(dev), torch.from_numpy(rd[sel])[None].to(dev)
-        for pipe, mode in (("fused", "infer"), ("fused", "train"), ("split", "infer"), ("split", "train")):
-            m.pipeline = pipe
+        for pipe, mode in (("fused", "train"), ("split", "train"), ("split-tc", "infer"), ("split-tc", "train")):
+            m.pipeline = pipe.split("-")[0]
+            m.set_mlp_fp16(pipe.endswith("tc"))
             eng.timing = {"fwd": [], "bwd": []}
             for it in range(3):
                 if mode == "infer":
@@ -37,7 +38,7 @@ for L in levels:
             b = [a.elapsed_time(b_) for a, b_ in eng.timing["bwd"]][1:]
             eng.timing = None
             fb, bb = bench.algorithmic_bytes(m.cfg)
-            msg = f"[probe] L={L} N={N} {pipe:5s} {mode}: fwd {np.mean(f):8.2f} ms ({N/np.mean(f)*1e3:9.0f} rays/s, {fb*N*768/np.mean(f)/1e6:7.0f} GB/s alg)"
+            msg = f"[probe] L={L} N={N} {pipe:8s} {mode}: fwd {np.mean(f):8.2f} ms ({N/np.mean(f)*1e3:9.0f} rays/s, {fb*N*768/np.mean(f)/1e6:7.0f} GB/s alg)"
             if b:
                 msg += f" | bwd {np.mean(b):8.2f} ms ({N/np.mean(b)*1e3:9.0f} rays/s, {bb*N*768/np.mean(b)/1e6:7.0f} GB/s alg) | fwd+bwd {N/(np.mean(f)+np.mean(b))*1e3:9.0f} rays/s"
             print(msg, flush=True)

@@ -73,6 +73,11 @@ extern "C" int hs_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, v
   C(m->flow_mlp[1], F(L.flo_w1), 64 * 64, 64 * 64);
   T(m->flow_mlp[2], 64, F(L.flo_w2t), 64, 8, 64, 6);
   C(m->flow_mlp[2], F(L.flo_w2), 6 * 64, 8 * 64);
+  if (cfg->mlp_fp16) {      // mirror of k_round_fp16 over the fp32 MLP working copies
+    float* w = F(L.sig_w1t);
+    const size_t n = (L.tc_sig_w1 - L.sig_w1t) / 4;
+    for (size_t i = 0; i < n; ++i) w[i] = __half2float(__float2half_rn(w[i]));
+  }
   return L4D_OK;
 }
 

@@ -39,10 +39,10 @@ def lib():
 class HostSim:
     """Holds staged params (host memory) for one oracle model."""
 
-    def __init__(self, oracle):
+    def __init__(self, oracle, mlp_fp16=False):
         self.L = lib()
         self.cfg = oracle.cfg
-        self.ccfg = _capi.make_config(self.cfg)
+        self.ccfg = _capi.make_config(self.cfg, mlp_fp16=mlp_fp16)
         self.params = {k: v.detach().contiguous().float() for k, v in oracle.ref_state_dict().items() if k != "aabb"}
         tab = _capi.L4DMasterParams()
         _capi.fill_pointer_table(tab, self.cfg, lambda n: self.params[n].data_ptr())

@@ -263,3 +263,36 @@ def test_tcgen05_selftest_gemm(dev, N, K):
     torch.cuda.synchronize()
     ref = A.float() @ B.float().t()
     assert rel_err(Cc, ref) < 1e-5
+
+
+TC_CASES = [(0.4, 200, False, 3, False), (0.0, 150, True, 4, False), (0.6, 260, True, 6, True), (0.4, 768, True, 27, False)]
+
+
+@pytest.mark.parametrize("t,S,perturb,seed,surface", TC_CASES)
+def test_tensor_core_path(dev, t, S, perturb, seed, surface):
+    """mlp_fp16 mode: the dense kernels run on tcgen05 tensor cores (fp16 hi/lo-split activations, fp16 weights,
+    fp32 TMEM accumulation).  The oracle emulates the fp16 weight rounding exactly; tolerance stays 1e-4."""
+    orc = O.build_seeded(small_config(), seed, flow_last_std=0.02)
+    if surface:
+        make_surface_like(orc)
+    orc.mlp_dtype = "fp16"
+    m = cuda_model_from_oracle(orc).set_mlp_fp16(True)
+    m.jitter_seed = seed
+    ro, rd = _rays(3, 8) if S < 700 else _rays(2, 5)
+    N = ro.shape[0]
+    ref = orc.render(torch.from_numpy(ro), torch.from_numpy(rd), t, num_steps=S, perturb=perturb, seed=seed,
+                     return_stages=True)
+    assert relu_margin(orc, ref) > MIN_RELU_MARGIN
+    out = m.render(torch.from_numpy(ro)[None].to(dev), torch.from_numpy(rd)[None].to(dev), torch.tensor([[t]]),
+                   staged=False, num_steps=S, perturb=perturb)
+    for k in ("depth_lidar", "image_lidar", "weights_sum_lidar", "weights"):
+        assert rel_err(out[k], ref[k]) < TOL, k
+    g = torch.Generator().manual_seed(1)
+    gd, gi = torch.randn(N, generator=g), torch.randn(N, 2, generator=g)
+    ((ref["depth_lidar"] * gd).sum() + (ref["image_lidar"] * gi).sum()).backward()
+    ((out["depth_lidar"][0] * gd.to(dev)).sum() + (out["image_lidar"][0] * gi.to(dev)).sum()).backward()
+    og = orc.ref_named_grads()
+    got = {k: p.grad for k, p in m.named_parameters()}
+    errs = {k: rel_err(got[k], g_ref) for k, g_ref in og.items() if g_ref.numel()}
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, f"worst {max(errs.values()):.2e}; failing: {bad}"

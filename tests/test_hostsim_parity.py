@@ -142,3 +142,28 @@ def test_edge_cases_empty_mask_and_single_step():
     assert not bool(ref["mask"].any())
     assert float(got["image"].abs().max()) == 0.0
     assert rel_err(got["depth"], ref["depth_lidar"]) < TOL or float(ref["depth_lidar"].abs().max()) < 1e-6
+
+
+def test_mlp_fp16_weight_mode():
+    """mlp_fp16: MLP weights are fp16-rounded working copies (tcnn keeps half params); the oracle emulates
+    the rounding exactly, so parity stays at 1e-4 for outputs and all gradients (straight-through to fp32 masters)."""
+    orc = O.build_seeded(small_config(), 12, flow_last_std=0.02)
+    orc.mlp_dtype = "fp16"
+    hs = H.HostSim(orc, mlp_fp16=True)
+    ro, rd = _rays()
+    N, S, t = ro.shape[0], 200, 0.4
+    ref = orc.render(torch.from_numpy(ro), torch.from_numpy(rd), t, num_steps=S, return_stages=True)
+    assert relu_margin(orc, ref) > MIN_RELU_MARGIN
+    got = hs.render(ro, rd, t, S, train=True)
+    for k, ko in [("depth", "depth_lidar"), ("image", "image_lidar"), ("weights", "weights")]:
+        assert rel_err(got[k], ref[ko]) < TOL, k
+    gd, gi = torch.linspace(0.5, 1.5, N), torch.stack([torch.linspace(-1, 1, N), torch.linspace(1, 0.2, N)], -1)
+    ((ref["depth_lidar"] * gd).sum() + (ref["image_lidar"] * gi).sum()).backward()
+    og, hg = orc.ref_named_grads(), hs.backward(gd, gi)
+    for k in hg:
+        if og[k].numel():
+            assert rel_err(hg[k], og[k]) < TOL, k
+    # and the rounding is visible: fp32-weight oracle differs by more than the parity tolerance
+    orc32 = O.build_seeded(small_config(), 12, flow_last_std=0.02)
+    ref32 = orc32.render(torch.from_numpy(ro), torch.from_numpy(rd), t, num_steps=S)
+    assert rel_err(ref32["depth_lidar"], ref["depth_lidar"]) > 1e-6
