@@ -167,6 +167,90 @@ L4D_HD void l4d_bw_sigma_c(const DevModel& M, const BwSample& s, const float* fe
 }
 
 // ---- B4: scatter dh through the encoders ------------------------------------------------
+// ---- warp-level pre-aggregation of plane gradients (device only) ---------------------------------
+// Lanes of a warp are consecutive samples of a ray: they hit the same plane texel in long runs (a
+// warp spans ~5 texels at resolution 256, <1 at 32).  The SM retires only ~1 fp32 RED per 1.3 cycles
+// (a RED.F32x4 counts as 4) and plane gradients are half of all atomics of the backward, so each run
+// is summed with a segmented warp scan and only its last lane issues the REDs.
+#if defined(__CUDACC__)
+struct WarpRuns {
+  int dist;     // lane - first lane of this lane's run of equal keys
+  bool tail;    // last lane of its run
+};
+__device__ __forceinline__ WarpRuns l4d_warp_runs(int key) {
+  const unsigned lane = threadIdx.x & 31u;
+  const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0u) || (prev != key);
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  const unsigned below = heads & (0xffffffffu >> (31u - lane));
+  WarpRuns r;
+  r.dist = (int)lane - (31 - __clz(below));
+  r.tail = (lane == 31u) || ((heads >> (lane + 1u)) & 1u);
+  return r;
+}
+__device__ __forceinline__ float l4d_seg_sum(float v, int dist) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, v, d);
+    if (dist >= d) v += t;
+  }
+  return v;
+}
+// all 32 lanes must call; g may be zero for lanes without a contribution
+__device__ __forceinline__ void l4d_plane_scatter_warp(float* G, int W, const Bilerp& b, const float g[8]) {
+  const WarpRuns r = l4d_warp_runs(b.y0 * W + b.x0);
+  const float wgt[4] = {b.wx0 * b.wy0, b.wx1 * b.wy0, b.wx0 * b.wy1, b.wx1 * b.wy1};
+  const int xs[4] = {b.x0, b.x1, b.x0, b.x1};
+  const int ys[4] = {b.y0, b.y0, b.y1, b.y1};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float s[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s[c] = l4d_seg_sum(g[c] * wgt[k], r.dist);
+    if (r.tail) {
+      float* p = G + ((size_t)ys[k] * W + xs[k]) * 8;
+      l4d_red4(p, s[0], s[1], s[2], s[3]);
+      l4d_red4(p + 4, s[4], s[5], s[6], s[7]);
+    }
+  }
+}
+// time planes: the y (time) weights are the same for every lane, so two sums per channel suffice
+__device__ __forceinline__ void l4d_plane_scatter_warp_t(float* G, int W, const Bilerp& b, const float g[8]) {
+  const WarpRuns r = l4d_warp_runs(b.x0);
+  float s0[8], s1[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { s0[c] = l4d_seg_sum(g[c] * b.wx0, r.dist); s1[c] = l4d_seg_sum(g[c] * b.wx1, r.dist); }
+  if (r.tail) {
+    float* p00 = G + ((size_t)b.y0 * W + b.x0) * 8;
+    float* p01 = G + ((size_t)b.y0 * W + b.x1) * 8;
+    float* p10 = G + ((size_t)b.y1 * W + b.x0) * 8;
+    float* p11 = G + ((size_t)b.y1 * W + b.x1) * 8;
+    l4d_red4(p00, s0[0] * b.wy0, s0[1] * b.wy0, s0[2] * b.wy0, s0[3] * b.wy0);
+    l4d_red4(p00 + 4, s0[4] * b.wy0, s0[5] * b.wy0, s0[6] * b.wy0, s0[7] * b.wy0);
+    l4d_red4(p01, s1[0] * b.wy0, s1[1] * b.wy0, s1[2] * b.wy0, s1[3] * b.wy0);
+    l4d_red4(p01 + 4, s1[4] * b.wy0, s1[5] * b.wy0, s1[6] * b.wy0, s1[7] * b.wy0);
+    if (b.wy1 != 0.f) {
+      l4d_red4(p10, s0[0] * b.wy1, s0[1] * b.wy1, s0[2] * b.wy1, s0[3] * b.wy1);
+      l4d_red4(p10 + 4, s0[4] * b.wy1, s0[5] * b.wy1, s0[6] * b.wy1, s0[7] * b.wy1);
+      l4d_red4(p11, s1[0] * b.wy1, s1[1] * b.wy1, s1[2] * b.wy1, s1[3] * b.wy1);
+      l4d_red4(p11 + 4, s1[4] * b.wy1, s1[5] * b.wy1, s1[6] * b.wy1, s1[7] * b.wy1);
+    }
+  }
+}
+#endif
+
+// plane-gradient sink: plain per-lane REDs, or the warp-aggregated version (device, full warps only)
+template <bool WARP_AGG>
+L4D_HD void l4d_plane_sink(float* G, int W, const Bilerp& b, const float g[8], bool time_plane) {
+#if defined(__CUDA_ARCH__)
+  if (WARP_AGG) {
+    if (time_plane) l4d_plane_scatter_warp_t(G, W, b, g); else l4d_plane_scatter_warp(G, W, b, g);
+    return;
+  }
+#endif
+  l4d_plane_scatter(G, W, b, g);
+}
+
 // where dL/dfeature comes from: recomputed on demand from dh (single-kernel path) or read from the
 // SoA plane the dense backward kernel wrote (split pipeline)
 struct DfeatFromDh {
@@ -181,21 +265,23 @@ struct DfeatFromPlane {
 };
 
 // scatter dL/dfeature through the encoders of one sample at (x,y,z) with its flow; dflow[6] out
-template <class DF>
+template <bool WARP_AGG, class DF>
 L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
-                             const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6]);
+                             const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6], bool active);
 
 L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads& G, BwSample& s) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) s.dflow[k] = 0.f;
   if (!s.active) return;
   DfeatFromDh df{&M, &s};
-  l4d_bw_scatter_t(M, F, G, s.x, s.y, s.z, s.flow, df, s.dflow);
+  l4d_bw_scatter_t<false>(M, F, G, s.x, s.y, s.z, s.flow, df, s.dflow, true);
 }
 
-template <class DF>
+// WARP_AGG: every lane of the warp must call (lanes without a sample pass active=false and a
+// provider that returns 0; they take part in the plane aggregation with zero contributions)
+template <bool WARP_AGG, class DF>
 L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
-                             const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6]) {
+                             const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6], bool active) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) dflow[k] = 0.f;
   const int nS = (int)M.n_scales;
@@ -222,13 +308,13 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
       l4d_plane_sample<false>(M.planes[sc][3], R, b2, v2, dummy);
 #pragma unroll
       for (int c = 0; c < 8; ++c) g[c] = d[c] * v1[c] * v2[c];
-      l4d_plane_scatter(G.planes_cl[sc][0], R, b0, g);
+      l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][0], R, b0, g, false);
 #pragma unroll
       for (int c = 0; c < 8; ++c) g[c] = d[c] * v0[c] * v2[c];
-      l4d_plane_scatter(G.planes_cl[sc][1], R, b1, g);
+      l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][1], R, b1, g, false);
 #pragma unroll
       for (int c = 0; c < 8; ++c) g[c] = d[c] * v0[c] * v1[c];
-      l4d_plane_scatter(G.planes_cl[sc][3], R, b2, g);
+      l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][3], R, b2, g, false);
     }
     {   // time planes (x,t) (y,t) (z,t): three queries, warped ones also feed d(coords) -> flow
       float d[8];
@@ -250,19 +336,20 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v1[c] * v2[c]; c0 = fmaf(g[c], x0[c], c0); }
-        l4d_plane_scatter(G.planes_cl[sc][2], R, b0, g);
+        l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][2], R, b0, g, true);
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v0[c] * v2[c]; c1 = fmaf(g[c], x1[c], c1); }
-        l4d_plane_scatter(G.planes_cl[sc][4], R, b1, g);
+        l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][4], R, b1, g, true);
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v0[c] * v1[c]; c2 = fmaf(g[c], x2[c], c2); }
-        l4d_plane_scatter(G.planes_cl[sc][5], R, b2, g);
+        l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][5], R, b2, g, true);
         if (qi == 1) { dflow[0] += c0; dflow[1] += c1; dflow[2] += c2; }
         if (qi == 2) { dflow[3] += c0; dflow[4] += c1; dflow[5] += c2; }
       }
     }
   }
 
+  if (!active) return;
   // static hash: dL/dtable[entry] += w_corner * dfeat[0..4)
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {

@@ -266,12 +266,24 @@ __global__ void __launch_bounds__(NT) k_bwd_dense(const __grid_constant__ SplitA
 // -------------------------------------------------------------------------------------------
 // backward 2/3: scatter dL/dfeature through the encoders (vector REDs), thread == sample.
 // -------------------------------------------------------------------------------------------
+struct DfeatFromPlaneMasked {
+  const float* base;
+  size_t stride;
+  bool on;
+  __device__ __forceinline__ float operator()(int row) const { return on ? __ldg(base + (size_t)row * stride) : 0.f; }
+};
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 4) k_bwd_scatter(const __grid_constant__ SplitArgs A) {
   const DevModel& M = A.M;
   const size_t P = A.sv.P;
   const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
-  for (size_t p = (size_t)blockIdx.x * NT + threadIdx.x; p < P; p += (size_t)gridDim.x * NT) {
+  for (size_t base = (size_t)blockIdx.x * NT; base < P; base += (size_t)gridDim.x * NT) {
+    // whole warps stay together (plane gradients are aggregated across lanes); lanes past the end
+    // shadow the last sample with zero gradient
+    const size_t pp = base + threadIdx.x;
+    const bool active = pp < P;
+    const size_t p = active ? pp : P - 1;
     const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
     const float zj = l4d_z(rs, A.ray_offset + ray, j);
     const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
@@ -280,10 +292,12 @@ __global__ void __launch_bounds__(NT, 4) k_bwd_scatter(const __grid_constant__ S
     float flow[6], dflow[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) flow[k] = A.sv.flow[(size_t)k * P + p];
-    DfeatFromPlane df{A.sv.dfeat + p, P};
-    l4d_bw_scatter_t(M, A.F, A.G, x, y, z, flow, df, dflow);
+    DfeatFromPlaneMasked df{A.sv.dfeat + p, P, active};
+    l4d_bw_scatter_t<true>(M, A.F, A.G, x, y, z, flow, df, dflow, active);
+    if (active) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) A.sv.dflow[(size_t)k * P + p] = dflow[k];
+      for (int k = 0; k < 6; ++k) A.sv.dflow[(size_t)k * P + p] = dflow[k];
+    }
   }
 }
 
