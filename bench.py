@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--rays", type=int, default=H_SWEEP * W_SWEEP, help="rays per step (sweep size)")
     ap.add_argument("--cpu-rays", type=int, default=64, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", default="split", choices=["split", "fused"])
+    ap.add_argument("--mlp", default="fp16", choices=["fp16", "fp32"],
+                    help="fp16: MLP weights as fp16 working copies (as tiny-cuda-nn), tensor-core dense kernels; fp32: FMA")
     return ap.parse_args()
 
 
@@ -233,7 +236,7 @@ def workload_config(args, note=None):
                      f"L={args.levels} 4D hash (2^19 static, 2^15/2^13/2^13 x8 time slices) + 6 hex-planes x4 scales + flow field, "
                      f"{N_FRAMES} frames",
          "rays_per_step": args.rays, "ray_batch": args.ray_batch, "n_levels_hash": args.levels,
-         "parallelism": f"ray-sharded dp{args.gpus}",
+         "parallelism": f"ray-sharded dp{args.gpus}", "pipeline": getattr(args, "pipeline", None), "mlp": getattr(args, "mlp", None),
          "l2": "inputs larger than L2: fp16/fp32 working set > 126 MB plus > 1 GB of saved activations streamed per step"}
     if note:
         c["note"] = note
@@ -263,6 +266,8 @@ def run_b200(args):
     model = LiDAR4D(**model_kwargs(args.levels)).to(dev)
     randomize(model, 0)
     model.materialize_weights = False            # weights/z_vals are only read by --urf_loss (runner.py:256-276)
+    model.pipeline = args.pipeline
+    model.set_mlp_fp16(args.mlp == "fp16")
     dp = RayShardedDP(model, world_size=world, rank=rank)
     opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True)
     n_rays, rb = args.rays, args.ray_batch
@@ -357,7 +362,7 @@ def run_b200(args):
     peak, peak_src = peaks()
     samples_per_launch = min(rb, n_rays) * S_STEPS
     kern = {}
-    for name, ts, b in (("k_render_fwd", t_f, fwd_b), ("k_render_bwd", t_b, bwd_b)):
+    for name, ts, b in (("forward (k_fwd_gather+k_fwd_dense*)" if args.pipeline == "split" else "k_render_fwd", t_f, fwd_b), ("backward (k_bwd_dense+k_bwd_scatter+k_bwd_flow)" if args.pipeline == "split" else "k_render_bwd", t_b, bwd_b)):
         if ts:
             avg = float(np.mean(ts))
             kern[name] = {"avg_ms": avg, "launches_timed": len(ts), "alg_bytes_per_sample": b,
@@ -374,7 +379,8 @@ def run_b200(args):
         "metric": "training rays/sec at 64x1024 rays x 768 samples", "value": value, "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp16 tables / fp32 planes, MLPs, compositing and gradients", "data": "synthetic",
+        "dtype": ("fp16 tables + fp16 MLP weights (tcgen05, hi/lo fp16 activations, fp32 accumulate)" if args.mlp == "fp16"
+                  else "fp16 tables, fp32 MLPs") + "; fp32 planes, compositing and gradients", "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n_rays * 6 * 4,
                 "d2h_bytes_per_step": n_rays * 3 * 4 + 4, "ms_per_step": ms_e2e / args.steps},

@@ -199,6 +199,10 @@ int    l4d_density_forward(const L4DConfig* cfg, const void* staged, const L4DFr
 /* tcgen05/TMEM self-test of the MLP engine's building blocks: C[128,N] = A[128,K] * B[N,K]^T,
  * fp16 operands, fp32 accumulate (N%16==0 in [16,256], K%16==0 in [16,512]). */
 int    l4d_tc_selftest(const void* A_half, const void* B_half, float* C, uint32_t N, uint32_t K, void* stream);
+/* same with operands pre-arranged in the engine's tile format, M in {64,128}, K-major or MN-major operands
+ * (the weight-gradient GEMMs X^T*delta read sample-major tiles as MN-major operands). */
+int    l4d_tc_selftest2(const void* A_tile, const void* B_tile, float* C, uint32_t M, uint32_t N, uint32_t K,
+                        uint32_t a_mn_major, uint32_t b_mn_major, void* stream);
 
 #ifdef __cplusplus
 }

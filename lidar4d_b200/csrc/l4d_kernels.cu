@@ -1005,3 +1005,18 @@ extern "C" int l4d_tc_selftest(const void* A, const void* B, float* Cout, uint32
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
+
+// tcgen05 self-test 2: operands pre-arranged in tile format; M in {64,128}; either operand may be MN-major
+extern "C" int l4d_tc_selftest2(const void* A, const void* B, float* Cout, uint32_t M, uint32_t N, uint32_t K,
+                                uint32_t a_mn, uint32_t b_mn, void* stream) {
+  if (!A || !B || !Cout) return l4d_fail(L4D_EINVAL, "null pointer");
+  if ((M != 64 && M != 128) || N < 8 || N > 256 || N % 8 || (M == 128 && N % 16) || K < 16 || K % 16 || K > 256)
+    return l4d_fail(L4D_EINVAL, "need M in {64,128}, N%8==0 (N%16 for M=128) <= 256, K%16==0 <= 256");
+  const size_t smem = (size_t)(((M * K * 2 + 1023) & ~1023u) + N * K * 2 + 2048);
+  L4D_CUDA(cudaFuncSetAttribute(k_tc_selftest2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tc_selftest2<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned char*>(A),
+                                                         reinterpret_cast<const unsigned char*>(B), Cout, (int)M, (int)N, (int)K,
+                                                         (int)a_mn, (int)b_mn);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}

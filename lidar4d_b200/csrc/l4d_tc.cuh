@@ -56,10 +56,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;
   return d;
 }
-// instruction descriptor: kind::f16, A/B = F16 K-major, D = F32, M x N
-__host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// instruction descriptor: kind::f16, A/B = F16, D = F32, M x N; a_mn / b_mn = 1 selects an MN-major operand
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// TMEM lane that holds accumulator row m: M=128 -> lane m; M=64 -> 16 lanes of every 32-lane sub-partition
+__host__ __device__ constexpr uint32_t tmem_lane_of_row(uint32_t M, uint32_t m) { return M == 64 ? (m & 15u) + 32u * (m >> 4) : m; }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, one K=16 step; issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -146,6 +148,59 @@ __global__ void __launch_bounds__(128) k_tc_selftest(const __half* __restrict__ 
     tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
 #pragma unroll
     for (int i = 0; i < 16; ++i) C[(size_t)tid * N + n0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
+// =============================================================================================
+// self-test 2: operands arrive already in tile format (prepared on the host), any major-ness, M = 64 or 128.
+//   K-major operand  X[rows][K]      : byte((k/8)*rows*16 + r*16 + (k%8)*2)           LBO = rows*16, SBO = 128
+//   MN-major operand X[rows=mn][K=k] : byte((mn/8)*K*16  + k*16 + (mn%8)*2)           LBO = 128,     SBO = K*16
+// =============================================================================================
+__global__ void __launch_bounds__(128) k_tc_selftest2(const unsigned char* __restrict__ A, const unsigned char* __restrict__ B,
+                                                      float* __restrict__ C, int M, int N, int K, int a_mn, int b_mn) {
+  using namespace l4dtc;
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int a_bytes = M * K * 2, b_bytes = N * K * 2;
+  unsigned char* sA = tc_smem;
+  unsigned char* sB = tc_smem + ((a_bytes + 1023) & ~1023);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  for (int i = tid * 16; i < a_bytes; i += 128 * 16) *reinterpret_cast<uint4*>(sA + i) = *reinterpret_cast<const uint4*>(A + i);
+  for (int i = tid * 16; i < b_bytes; i += 128 * 16) *reinterpret_cast<uint4*>(sB + i) = *reinterpret_cast<const uint4*>(B + i);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = idesc_f16((uint32_t)M, (uint32_t)N, (uint32_t)a_mn, (uint32_t)b_mn);
+    for (int k = 0; k < K / 16; ++k) {
+      const uint64_t da = a_mn ? smem_desc(smem_u32(sA) + (uint32_t)k * 256u, 128u, (uint32_t)K * 16u)
+                               : smem_desc(smem_u32(sA) + (uint32_t)(2 * k) * (uint32_t)M * 16u, (uint32_t)M * 16u, 128u);
+      const uint64_t db = b_mn ? smem_desc(smem_u32(sB) + (uint32_t)k * 256u, 128u, (uint32_t)K * 16u)
+                               : smem_desc(smem_u32(sB) + (uint32_t)(2 * k) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+      umma_f16(tbase, da, db, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  // every lane of the warp's sub-partition is read; only lanes that hold a row store it
+  for (int n0 = 0; n0 < N; n0 += 16) {
+    float v[16];
+    tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
+    int row = -1;
+    if (M == 128) row = tid; else if (lane < 16) row = warp * 16 + lane;
+    if (row >= 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (n0 + i < N) C[(size_t)row * N + n0 + i] = v[i];
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -296,3 +296,32 @@ def test_tensor_core_path(dev, t, S, perturb, seed, surface):
     errs = {k: rel_err(got[k], g_ref) for k, g_ref in og.items() if g_ref.numel()}
     bad = {k: v for k, v in errs.items() if not v < TOL}
     assert not bad, f"worst {max(errs.values()):.2e}; failing: {bad}"
+
+
+def _tile_kmajor(X):       # X [rows][K] fp16 -> [K/8][rows][8]
+    rows, K = X.shape
+    return X.view(rows, K // 8, 8).permute(1, 0, 2).contiguous()
+
+
+def _tile_mnmajor(X):      # X [rows=mn][K] fp16 -> [mn/8][K][8]
+    rows, K = X.shape
+    return X.view(rows // 8, 8, K).permute(0, 2, 1).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(128, 64, 128, 0, 0), (128, 64, 128, 1, 0), (128, 64, 64, 0, 1), (128, 176, 64, 0, 1),
+                                             (128, 64, 128, 1, 1), (64, 64, 128, 1, 1), (64, 16, 128, 1, 1), (64, 8, 128, 1, 1),
+                                             (64, 64, 64, 0, 0), (128, 16, 16, 0, 1)])
+def test_tcgen05_selftest_layouts(dev, M, N, K, a_mn, b_mn):
+    """MN-major operands (sample-major tiles read transposed) and M=64 accumulators, as the tensor-core backward uses them."""
+    from lidar4d_b200 import _capi
+    lib = _capi.load_library()
+    g = torch.Generator().manual_seed(M + 7 * N + 13 * K + a_mn + 2 * b_mn)
+    A = torch.randn(M, K, generator=g).half()
+    B = torch.randn(N, K, generator=g).half()
+    At = (_tile_mnmajor(A) if a_mn else _tile_kmajor(A)).to(dev)
+    Bt = (_tile_mnmajor(B) if b_mn else _tile_kmajor(B)).to(dev)
+    Cc = torch.zeros(M, N, device=dev)
+    rc = lib.l4d_tc_selftest2(At.data_ptr(), Bt.data_ptr(), Cc.data_ptr(), M, N, K, a_mn, b_mn, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.l4d_last_error()
+    torch.cuda.synchronize()
+    assert rel_err(Cc, A.float() @ B.float().t()) < 1e-5
