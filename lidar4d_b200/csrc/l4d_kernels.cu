@@ -170,6 +170,7 @@ extern "C" int l4d_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, 
   for (int n = 0; n < 2; ++n) {
     k_pack_umma<<<nblk(64 * 15), 256, 0, st>>>(att[n], ap, 64, L4D_ENC, 15, H(L.tc_att_w1g), 128, n * 64);
     k_pack_umma<<<nblk(64 * 64), 256, 0, st>>>(att[n] + 64 * ap, 64, 64, 0, 64, H(L.tc_att_w2[n]), 64, 0);
+    k_pack_umma<<<nblk(64 * 16), 256, 0, st>>>(att[n], ap, 64, L4D_ENC, 16, H(L.tc_att_w1g_net[n]), 64, 0);
   }
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
@@ -868,7 +869,13 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
     A.train = 1u;
     const size_t P = (size_t)rays->n_rays * rays->n_steps;
     const uint32_t tiles = (uint32_t)((P + L4D_NT - 1) / L4D_NT);
-    {
+    if (cfg->mlp_fp16 && cfg->sigma_in_pad <= 192) {
+      const size_t smem = dense_bwd_smem(cfg->sigma_in_pad).total + 1024;
+      int grid;
+      rc = grid_for(k_bwd_dense_tc, 128, smem, rays->n_rays, grid);
+      if (rc != L4D_OK) return rc;
+      k_bwd_dense_tc<<<grid, 128, smem, st>>>(A);
+    } else {
       const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD + 80 + 128 + 128 + 32 + L4D_MAX_TILES) * sizeof(float);
       int grid;
       rc = grid_for(k_bwd_dense<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
