@@ -336,12 +336,12 @@ __device__ __forceinline__ float block_amax128(float v, float* s_w) {
   __syncthreads();
   return r;
 }
-// power-of-two scale that maps amax into [2^-5, 2^-4)
-__device__ __forceinline__ void pow2_scale(float amax, float& s, float& inv) {
+// power-of-two factor r that maps amax into [2^5, 2^6): fp16 hi+lo then resolve the tile to ~2^-30 of its
+// largest element while leaving 2^10 of headroom below the fp16 maximum
+__device__ __forceinline__ float pow2_factor(float amax) {
   int e;
   frexpf(amax, &e);
-  s = ldexpf(1.0f, -e - 4);
-  inv = ldexpf(1.0f, e + 4);
+  return ldexpf(1.0f, 6 - e);
 }
 }  // namespace l4dtc
 
@@ -376,9 +376,15 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
   float* s_csum = s_cdir2 + 128;
   float* s_w = s_csum + 128;
   float* s_tstart = s_w + 32;
+  __shared__ float s_w3max[2];
 
   if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&s_tmem, 512);
+  if (tid < 2) {
+    float m = 1.0f;
+    for (int k = 0; k < 64; ++k) m = fmaxf(m, fabsf(l4d_ld1(M.att_w3[tid] + k)));
+    s_w3max[tid] = m;
+  }
   {
     auto cp = [&](uint32_t off, const __half* src, uint32_t bytes) {
       for (uint32_t i = tid * 16; i < bytes; i += 128 * 16)
@@ -528,10 +534,7 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
         }
 #pragma unroll 1
         for (int net = 0; net < 2; ++net) {
-          const float amax = block_amax128(da[net], s_w);
-          if (amax == 0.f) continue;
-          float sc, inv;
-          pow2_scale(amax, sc, inv);
+          if (block_amax128(da[net], s_w) == 0.f) continue;       // no gradient reaches this head in this tile
           ms.publish();
           if (tid == 0) {
             mma_chunks(tm + 0, aG16h, sb + L.wa1[net], 64, 2, false);
@@ -562,6 +565,7 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
             ms.commit();
           }
           ms.wait();
+          float cs = 1.0f;
           {   // output layer (fp32), sigmoid backward, delta of the second hidden layer
             float o = 0.f;
             uint32_t m2a = 0u, m2b = 0u;
@@ -581,7 +585,11 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
               tile_put8(t2h, t2l, tid, 2 * q + 1, v + 8);
             }
             const float a = l4d_sigmoid(o);
-            const float d_o = masked ? da[net] * a * (1.0f - a) * sc : 0.f;
+            const float d_raw = masked ? da[net] * a * (1.0f - a) : 0.f;
+            // per-tile power-of-two scale of the delta tiles (|w3| <= w3max bounds the second tile too)
+            const float am = block_amax128(d_raw * s_w3max[net], s_w);
+            cs = am > 0.f ? pow2_factor(am) : 1.0f;
+            const float d_o = d_raw * cs;
             float d8[8] = {d_o, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             tile_put8(o8h, o8l, tid, 0, d8);
 #pragma unroll
@@ -611,15 +619,31 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
             ms.commit();
           }
           ms.wait();
+          const float inv = 1.0f / cs;
+          float cs2;
+          {   // re-scale the propagated delta with its own amax, then dH1 * relu1 -> T2 (H2 is dead)
+            float am = 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {       // dH1 * relu1 -> T2 (H2 is dead)
-            float v[16];
-            tmem_ld16(tlane + (uint32_t)(q * 16), v);
+            for (int q = 0; q < 4; ++q) {
+              float v[16];
+              tmem_ld16(tlane + (uint32_t)(q * 16), v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = l4d_bit(m1a, m1b, q * 16 + i) ? v[i] : 0.f;
-            tile_put8(t2h, t2l, tid, 2 * q, v);
-            tile_put8(t2h, t2l, tid, 2 * q + 1, v + 8);
+              for (int i = 0; i < 16; ++i) if (l4d_bit(m1a, m1b, q * 16 + i)) am = fmaxf(am, fabsf(v[i]));
+            }
+            am = block_amax128(am, s_w);
+            const float r = am > 0.f ? pow2_factor(am) : 1.0f;
+            cs2 = cs * r;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v[16];
+              tmem_ld16(tlane + (uint32_t)(q * 16), v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = l4d_bit(m1a, m1b, q * 16 + i) ? v[i] * r : 0.f;
+              tile_put8(t2h, t2l, tid, 2 * q, v);
+              tile_put8(t2h, t2l, tid, 2 * q + 1, v + 8);
+            }
           }
+          const float inv2 = 1.0f / cs2;
           {   // flush dw3 and dW2^T (rows live in lanes < 16 of every warp)
             float v[16];
             tmem_ld16(tlane + 176u, v);        // 8 valid columns; column 0 = dw3[row]
@@ -649,12 +673,12 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
             float v[16];
             tmem_ld16(tlane + 128u, v);
 #pragma unroll
-            for (int i = 0; i < 15; ++i) dgeo[i] = fmaf(v[i], inv, dgeo[i]);
+            for (int i = 0; i < 15; ++i) dgeo[i] = fmaf(v[i], inv2, dgeo[i]);
             tmem_ld16(tlane + 160u, v);
             if (has64) {
 #pragma unroll
-              for (int i = 0; i < 15; ++i) atomicAdd(G.att_w1t[net] + (size_t)(L4D_ENC + i) * 64 + row64, v[i] * inv);
-              s_csum[net * 64 + row64] += v[15] * inv;
+              for (int i = 0; i < 15; ++i) atomicAdd(G.att_w1t[net] + (size_t)(L4D_ENC + i) * 64 + row64, v[i] * inv2);
+              s_csum[net * 64 + row64] += v[15] * inv2;
             }
           }
           tc_fence_before();
@@ -679,8 +703,8 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
         tc_fence_after();
         continue;
       }
-      float sc, inv;
-      pow2_scale(amax, sc, inv);
+      const float sc = pow2_factor(amax);
+      float inv = 1.0f / sc;
 #pragma unroll
       for (int i = 0; i < 16; ++i) d16[i] *= sc;
       tile_put8(o16h, o16l, tid, 0, d16);
@@ -697,21 +721,34 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
         ms.commit();
       }
       ms.wait();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {         // dHs * relu -> RH (hidden is dead)
-        float v[16];
-        tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = l4d_bit(msa, msb, q * 16 + i) ? v[i] : 0.f;
-        tile_put8(hh, hl, tid, 2 * q, v);
-        tile_put8(hh, hl, tid, 2 * q + 1, v + 8);
-      }
       {
         float v[16];
         tmem_ld16(tlane + 144u, v);
         if (has64) {
 #pragma unroll
           for (int o = 0; o < 16; ++o) atomicAdd(G.sig_w2 + (size_t)o * 64 + row64, v[o] * inv);
+        }
+      }
+      {   // re-scale the propagated delta with its own amax, then dHs * relu -> RH (hidden is dead)
+        float am2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[16];
+          tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (l4d_bit(msa, msb, q * 16 + i)) am2 = fmaxf(am2, fabsf(v[i]));
+        }
+        am2 = block_amax128(am2, s_w);
+        const float r = am2 > 0.f ? pow2_factor(am2) : 1.0f;
+        inv = 1.0f / (sc * r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[16];
+          tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = l4d_bit(msa, msb, q * 16 + i) ? v[i] * r : 0.f;
+          tile_put8(hh, hl, tid, 2 * q, v);
+          tile_put8(hh, hl, tid, 2 * q + 1, v + 8);
         }
       }
       // ---------------- P4: input gradients and first-layer weight gradient ----------------
