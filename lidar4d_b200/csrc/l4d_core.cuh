@@ -59,7 +59,7 @@ struct DevGrid {
 struct DevModel {
   DevGrid gs, gd[3], gf;
   const __half* hs;             // static table   [entries][4]
-  const __half* hd[3];          // dynamic tables [slice][entries][4]
+  const __half* hd[3];          // dynamic tables [pair k = slices k,k+1][entries][lo 4 | hi 4]
   const __half* hf;             // flow table     [entries][8]
   uint32_t hd_slice_entries[3]; // entries per time slice
   const float* planes[L4D_MAX_PLANE_SCALES][6];   // channels-last [H][W][8]
@@ -269,36 +269,37 @@ L4D_HD void l4d_encode3_f8(const DevGrid& g, const __half* table, int l, float x
 }
 
 // one level of one time-sliced 2D grid at (x,y): blend of slices lo/hi, then the
-// cubic Lagrange contraction over the 4 features -> 1 value (hash_field.py:65-88)
-L4D_HD float l4d_encode2_time(const DevGrid& g, const __half* table, uint32_t slice_entries,
+// cubic Lagrange contraction over the 4 features -> 1 value (hash_field.py:65-88).
+// Working layout: "pair" k holds slices k and k+1 of every entry in ONE 16-byte record
+// {lo.f0..f3, hi.f0..f3} (fp16), so a corner costs one LDG.128 instead of two LDG.64 - the dynamic
+// hash is 2/3 of the forward's divergent gathers.  table = [pair][entries][8 halves].
+L4D_HD float l4d_encode2_time(const DevGrid& g, const __half* table, uint32_t slice_entries, uint32_t n_slices,
                               const L4DTimeQuery& q, int l, float x, float y) {
   uint32_t idx[4]; float w[4];
   l4d_corners2(g, l, x, y, idx, w);
-  const uint2* lo = reinterpret_cast<const uint2*>(table) + (size_t)q.slice_lo * slice_entries + g.offset[l];
-  const uint2* hi = reinterpret_cast<const uint2*>(table) + (size_t)q.slice_hi * slice_entries + g.offset[l];
-  uint2 vl[4], vh[4];
+  const uint32_t pair = q.slice_lo < n_slices - 1u ? q.slice_lo : n_slices - 2u;
+  // idx1 == idx2 (hash_field.py:82): the feature is G_lo alone; expressed as exact 1/0 weights on the pair
+  const float wl = q.single ? (q.slice_lo == pair ? 1.0f : 0.0f) : q.w_lo;
+  const float wh = q.single ? 1.0f - wl : q.w_hi;
+  const uint4* base = reinterpret_cast<const uint4*>(table) + (size_t)pair * slice_entries + g.offset[l];
+  uint4 v[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) vl[c] = l4d_ld_u2(lo + idx[c]);
-  if (!q.single) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) vh[c] = l4d_ld_u2(hi + idx[c]);
-  }
+  for (int c = 0; c < 4; ++c) v[c] = l4d_ld_u4(base + idx[c]);
   float fl[4] = {0.f, 0.f, 0.f, 0.f}, fh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    float2 a = l4d_h2f(vl[c].x), b = l4d_h2f(vl[c].y);
+    float2 a = l4d_h2f(v[c].x), b = l4d_h2f(v[c].y), cc = l4d_h2f(v[c].z), d = l4d_h2f(v[c].w);
     fl[0] = fmaf(w[c], a.x, fl[0]); fl[1] = fmaf(w[c], a.y, fl[1]);
     fl[2] = fmaf(w[c], b.x, fl[2]); fl[3] = fmaf(w[c], b.y, fl[3]);
+    fh[0] = fmaf(w[c], cc.x, fh[0]); fh[1] = fmaf(w[c], cc.y, fh[1]);
+    fh[2] = fmaf(w[c], d.x, fh[2]); fh[3] = fmaf(w[c], d.y, fh[3]);
   }
-  if (!q.single) {
+  if (q.single) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float2 a = l4d_h2f(vh[c].x), b = l4d_h2f(vh[c].y);
-      fh[0] = fmaf(w[c], a.x, fh[0]); fh[1] = fmaf(w[c], a.y, fh[1]);
-      fh[2] = fmaf(w[c], b.x, fh[2]); fh[3] = fmaf(w[c], b.y, fh[3]);
-    }
+    for (int i = 0; i < 4; ++i) fl[i] = wl != 0.f ? fl[i] : fh[i];
+  } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) fl[i] = q.w_lo * fl[i] + q.w_hi * fh[i];
+    for (int i = 0; i < 4; ++i) fl[i] = wl * fl[i] + wh * fh[i];
   }
   return ((q.basis[0] * fl[0] + q.basis[1] * fl[1]) + q.basis[2] * fl[2]) + q.basis[3] * fl[3];
 }
@@ -648,9 +649,9 @@ L4D_HD void l4d_gather_features(const DevModel& M, const L4DFrame& F, float x, f
     const float ba = p == 2 ? xw1 : xw0, bb = p == 0 ? xw1 : xw2;
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
-      float v = wc * l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], F.cur, l, ca, cb);
-      if (wf != 0.f) v = fmaf(wf, l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], F.fwd, l, fa, fb), v);
-      if (wb != 0.f) v = fmaf(wb, l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], F.bwd, l, ba, bb), v);
+      float v = wc * l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], M.time_res, F.cur, l, ca, cb);
+      if (wf != 0.f) v = fmaf(wf, l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], M.time_res, F.fwd, l, fa, fb), v);
+      if (wb != 0.f) v = fmaf(wb, l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], M.time_res, F.bwd, l, ba, bb), v);
       xb[l * xs] = v;
     }
     l4d_emit<ACC>(acc, M, xb, xs, row_hash_d + p * L, L, sink);

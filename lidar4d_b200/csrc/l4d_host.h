@@ -41,7 +41,7 @@ static inline StagedLayout staged_layout(const L4DConfig* c) {
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   L.hs = take((size_t)c->hash_static.offset[c->hash_static.n_levels] * 4 * sizeof(__half));
   for (int p = 0; p < 3; ++p)
-    L.hd[p] = take((size_t)c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels] * 4 * sizeof(__half) * c->time_resolution);
+    L.hd[p] = take((size_t)c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels] * 8 * sizeof(__half) * (c->time_resolution - 1));
   L.hf = take((size_t)c->flow.offset[c->flow.n_levels] * 8 * sizeof(__half));
   for (uint32_t s = 0; s < c->n_plane_scales; ++s)
     for (int ci = 0; ci < 6; ++ci) {

@@ -45,6 +45,20 @@ __global__ void k_cast_half(const float* __restrict__ src, __half* __restrict__ 
     reinterpret_cast<uint2*>(dst)[i] = o;
   }
 }
+// two fp32 time slices -> one fp16 pair record per entry {lo.f0..3, hi.f0..3}
+__global__ void k_pack_pair(const float* __restrict__ lo, const float* __restrict__ hi, uint4* __restrict__ dst, size_t n_entries) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n_entries; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(lo) + i), b = __ldg(reinterpret_cast<const float4*>(hi) + i);
+    __half2 a0 = __floats2half2_rn(a.x, a.y), a1 = __floats2half2_rn(a.z, a.w);
+    __half2 b0 = __floats2half2_rn(b.x, b.y), b1 = __floats2half2_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a0); o.y = *reinterpret_cast<uint32_t*>(&a1);
+    o.z = *reinterpret_cast<uint32_t*>(&b0); o.w = *reinterpret_cast<uint32_t*>(&b1);
+    dst[i] = o;
+  }
+}
 // NCHW [8][H*W] -> channels-last [H*W][8]
 __global__ void k_plane_to_cl(const float* __restrict__ src, float* __restrict__ dst, int hw) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,11 +136,12 @@ extern "C" int l4d_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, 
     k_cast_half<<<2048, 256, 0, st>>>(m->hash_static, H(L.hs), n);
   }
   for (int p = 0; p < 3; ++p) {
-    size_t n = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels] * 4;
-    for (uint32_t s = 0; s < cfg->time_resolution; ++s) {
+    const size_t ne = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels];
+    for (uint32_t s = 0; s < cfg->time_resolution; ++s)
       if (!m->hash_dynamic[p][s]) return l4d_fail(L4D_EINVAL, "null hash_dynamic slice");
-      k_cast_half<<<512, 256, 0, st>>>(m->hash_dynamic[p][s], H(L.hd[p]) + (size_t)s * n, n);
-    }
+    for (uint32_t s = 0; s + 1 < cfg->time_resolution; ++s)
+      k_pack_pair<<<512, 256, 0, st>>>(m->hash_dynamic[p][s], m->hash_dynamic[p][s + 1],
+                                        reinterpret_cast<uint4*>(b + L.hd[p]) + (size_t)s * ne, ne);
   }
   {
     size_t n = (size_t)cfg->flow.offset[cfg->flow.n_levels] * 8;

@@ -38,9 +38,16 @@ extern "C" int hs_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, v
   char* b = (char*)staged;
   auto cast = [&](const float* src, __half* dst, size_t n) { for (size_t i = 0; i < n; ++i) dst[i] = __float2half_rn(src[i]); };
   cast(m->hash_static, (__half*)(b + L.hs), (size_t)cfg->hash_static.offset[cfg->hash_static.n_levels] * 4);
-  for (int p = 0; p < 3; ++p) {
-    size_t n = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels] * 4;
-    for (uint32_t s = 0; s < cfg->time_resolution; ++s) cast(m->hash_dynamic[p][s], (__half*)(b + L.hd[p]) + s * n, n);
+  for (int p = 0; p < 3; ++p) {      // pair records {slice k F4, slice k+1 F4}
+    const size_t ne = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels];
+    for (uint32_t s = 0; s + 1 < cfg->time_resolution; ++s) {
+      __half* dst = (__half*)(b + L.hd[p]) + (size_t)s * ne * 8;
+      for (size_t e = 0; e < ne; ++e)
+        for (int f = 0; f < 4; ++f) {
+          dst[e * 8 + f] = __float2half_rn(m->hash_dynamic[p][s][e * 4 + f]);
+          dst[e * 8 + 4 + f] = __float2half_rn(m->hash_dynamic[p][s + 1][e * 4 + f]);
+        }
+    }
   }
   cast(m->flow_grid, (__half*)(b + L.hf), (size_t)cfg->flow.offset[cfg->flow.n_levels] * 8);
   for (uint32_t s = 0; s < cfg->n_plane_scales; ++s)
