@@ -393,24 +393,38 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
 }
 
 // ---- B5: flow MLP backprop.  g[6] = dL/dflow of this sample. ----------------------------
-// step a: recompute h1,h2 ; TA row[0..8) <- g ; TB row <- h2 ; xb keeps h1
-L4D_HD void l4d_bw_flow_a(const DevModel& M, const BwSample& s, const float* flow_in, size_t stride,
-                          const float g[6], float* xb, int xs, float* ta_row, float* tb_row) {
+// step a: recompute h1,h2 (and their relu patterns when RECORD) ; TA row[0..8) <- g ; TB row <- h2 ; xb keeps h1
+template <bool RECORD>
+L4D_HD void l4d_bw_flow_a_t(const DevModel& M, BwSample& s, const float* flow_in, size_t stride,
+                            const float g[6], float* xb, int xs, float* ta_row, float* tb_row) {
   float yv[L4D_H];
 #pragma unroll
   for (int k = 0; k < L4D_FLOW_IN; ++k) xb[k * xs] = s.active ? flow_in[(size_t)k * stride] : 0.f;
 #pragma unroll
   for (int k = 0; k < L4D_H; ++k) yv[k] = 0.f;
   l4d_layer64(yv, xb, xs, L4D_FLOW_IN, M.flo_w0t);
+  if (RECORD) {
+    l4d_relu_store(yv, xb, xs, s.mf1a, s.mf1b);                               // h1
+  } else {
 #pragma unroll
-  for (int k = 0; k < L4D_H; ++k) xb[k * xs] = fmaxf(yv[k], 0.f);            // h1
+    for (int k = 0; k < L4D_H; ++k) xb[k * xs] = fmaxf(yv[k], 0.f);           // h1
+  }
 #pragma unroll
   for (int k = 0; k < L4D_H; ++k) yv[k] = 0.f;
   l4d_layer64(yv, xb, xs, L4D_H, M.flo_w1t);
+  if (RECORD) { s.mf2a = 0u; s.mf2b = 0u; }
 #pragma unroll
-  for (int k = 0; k < L4D_H; ++k) tb_row[k] = s.active ? fmaxf(yv[k], 0.f) : 0.f;   // h2
+  for (int k = 0; k < L4D_H; ++k) {
+    const bool on = yv[k] > 0.f;
+    if (RECORD) { if (k < 32) s.mf2a |= on ? (1u << k) : 0u; else s.mf2b |= on ? (1u << (k - 32)) : 0u; }
+    tb_row[k] = (s.active && on) ? yv[k] : 0.f;                               // h2
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) ta_row[k] = (s.active && k < 6) ? g[k] : 0.f;
+}
+L4D_HD void l4d_bw_flow_a(const DevModel& M, const BwSample& s, const float* flow_in, size_t stride,
+                          const float g[6], float* xb, int xs, float* ta_row, float* tb_row) {
+  l4d_bw_flow_a_t<false>(M, const_cast<BwSample&>(s), flow_in, stride, g, xb, xs, ta_row, tb_row);
 }
 // step b: dh2 = (W2^T g) * relu2 ; TB row <- dh2 ; TA row <- h1 (from xb) ; xb <- dh2
 L4D_HD void l4d_bw_flow_b(const DevModel& M, const BwSample& s, const float g[6], float* xb, int xs,

@@ -153,14 +153,20 @@ __global__ void __launch_bounds__(128) k_fwd_dense_tc(const __grid_constant__ Sp
       const bool valid = j < S;
       const size_t p = (size_t)ray * S + (valid ? j : 0);
       // ---- features -> hi/lo tile (coalesced SoA reads, one 16-byte chunk per 8 features) ----
-      for (int c = 0; c < n_xchunks; ++c) {
-        float v[8];
+      // 4 chunks (32 independent coalesced loads) in flight per thread: with 4 warps per SM the HBM round trip
+      // has to be covered by memory-level parallelism inside the thread
+      for (int c0 = 0; c0 < n_xchunks; c0 += 4) {
+        float v[4][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = c * 8 + i;
-          v[i] = !valid ? 0.f : (k < (int)M.sigma_in_dim ? A.sv.feat[(size_t)k * A.sv.P + p] : 1.0f);
-        }
-        tile_put8(xh, xl, tid, c, v);
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = (c0 + cc) * 8 + i;
+            v[cc][i] = (!valid || k >= (int)in_pad) ? 0.f : (k < (int)M.sigma_in_dim ? __ldg(A.sv.feat + (size_t)k * A.sv.P + p) : 1.0f);
+          }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          if (c0 + cc < n_xchunks) tile_put8(xh, xl, tid, c0 + cc, v[cc]);
       }
       ms.publish();
       if (tid == 0) {
@@ -411,14 +417,17 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
 
   // features of this thread's sample -> X tile (24 chunks, zero beyond in_pad)
   auto load_x = [&](size_t p, bool valid) {
-    for (int c = 0; c < 24; ++c) {
-      float v[8];
+    for (int c0 = 0; c0 < 24; c0 += 4) {      // 32 independent loads in flight per thread (see k_fwd_dense_tc)
+      float v[4][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = c * 8 + i;
-        v[i] = (!valid || k >= (int)in_pad) ? 0.f : (k < (int)M.sigma_in_dim ? A.sv.feat[(size_t)k * A.sv.P + p] : 1.0f);
-      }
-      tile_put8(xh, xl, tid, c, v);
+      for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = (c0 + cc) * 8 + i;
+          v[cc][i] = (!valid || k >= (int)in_pad) ? 0.f : (k < (int)M.sigma_in_dim ? __ldg(A.sv.feat + (size_t)k * A.sv.P + p) : 1.0f);
+        }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tile_put8(xh, xl, tid, c0 + cc, v[cc]);
     }
   };
 

@@ -334,8 +334,7 @@ __global__ void __launch_bounds__(NT) k_bwd_flow(const __grid_constant__ SplitAr
       for (int k = 0; k < 6; ++k) g[k] = A.sv.dflow[(size_t)k * P + p];
     }
     __syncthreads();
-    l4d_bw_flow_fwd(M, s, A.sv.flow_in + p, P, xb, NT);
-    l4d_bw_flow_a(M, s, A.sv.flow_in + p, P, g, xb, NT, ta_row, tb_row);
+    l4d_bw_flow_a_t<true>(M, s, A.sv.flow_in + p, P, g, xb, NT, ta_row, tb_row);   // also records the relu patterns
     __syncthreads();
     tile_outer_accum<NT>(TA, TB, 8, A.G.flo_w2);
     __syncthreads();
