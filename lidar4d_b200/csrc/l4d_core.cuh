@@ -71,6 +71,7 @@ struct DevModel {
   const float *flo_w0t, *flo_w1t, *flo_w1, *flo_w2t, *flo_w2;
   // fp16 copies in the tcgen05 K-major interleaved layout [k/8][row n][8 halves] (element (n,k) = W[n][k])
   const __half *tc_sig_w1, *tc_sig_w2, *tc_att_w1g, *tc_att_w2[2], *tc_att_w1g_net[2];
+  const __half *tc_flo_w0, *tc_flo_w1, *tc_flo_w2;     // [2][64][8], [8][64][8], [8][16][8] (rows 6..15 zero)
   uint32_t mlp_fp16;
   uint32_t sigma_in_dim, sigma_in_pad, attr_in_dim, attr_in_pad, view_degree, active_sensor;
   float bound, near_lidar, far_lidar, density_scale;

@@ -828,3 +828,369 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
   __syncthreads();
   if (warp == 0) tmem_dealloc(tm, 512);
 }
+
+// =============================================================================================
+// flow MLP (16 -> 64 -> 64 -> 6) on tensor cores
+// =============================================================================================
+struct FlowTcSmem {
+  uint32_t w0, w1, w2;       // weights
+  uint32_t fin;              // 16-wide tile hi|lo (2 x 4 KB)
+  uint32_t t1, t2, t3;       // 64-wide tiles hi|lo (32 KB each); the forward uses t1 only
+  uint32_t do16;             // 16-wide delta tile hi|lo
+  uint32_t total_fwd, total;
+};
+__host__ __device__ inline FlowTcSmem flow_tc_smem() {
+  FlowTcSmem L;
+  uint32_t o = 0;
+  auto take = [&](uint32_t b) { uint32_t r = o; o += (b + 127u) & ~127u; return r; };
+  L.w0 = take(16 * 64 * 2); L.w1 = take(64 * 64 * 2); L.w2 = take(64 * 16 * 2);
+  L.fin = take(2 * 4096);
+  L.t1 = take(32 * 1024);
+  L.total_fwd = o;
+  L.t2 = take(32 * 1024); L.t3 = take(32 * 1024);
+  L.do16 = take(2 * 4096);
+  L.total = o;
+  return L;
+}
+
+namespace l4dtc {
+__device__ __forceinline__ void flow_copy_weights(unsigned char* dsm, const FlowTcSmem& L, const DevModel& M) {
+  auto cp = [&](uint32_t off, const __half* src, uint32_t bytes) {
+    for (uint32_t i = threadIdx.x * 16; i < bytes; i += 128 * 16)
+      *reinterpret_cast<uint4*>(dsm + off + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(src) + i));
+  };
+  cp(L.w0, M.tc_flo_w0, 16 * 64 * 2);
+  cp(L.w1, M.tc_flo_w1, 64 * 64 * 2);
+  cp(L.w2, M.tc_flo_w2, 64 * 16 * 2);
+}
+
+// flow MLP forward for the 128 samples of the CTA.  fin[16] per thread in, flow[8] out (6 used).
+// TMEM: [tm, tm+64) layer 1, [tm+64, tm+128) layer 2, [tm, tm+16) output.  Optionally returns the relu patterns
+// and leaves relu(layer-2) in tile t1 and (when H1_OUT) relu(layer-1) in tile h1_out.
+template <bool H1_OUT>
+__device__ __forceinline__ void flow_forward_tc(unsigned char* dsm, uint32_t sb, const FlowTcSmem& L, MmaSync& ms, uint32_t tm,
+                                                uint32_t tlane, const float (&fin)[16], float (&flow)[8], uint32_t& m1a,
+                                                uint32_t& m1b, uint32_t& m2a, uint32_t& m2b, unsigned char* h1_hi,
+                                                unsigned char* h1_lo, uint32_t a_h1_hi, uint32_t a_h1_lo) {
+  const int tid = threadIdx.x;
+  unsigned char *fh = dsm + L.fin, *fl = fh + 4096, *t1h = dsm + L.t1, *t1l = t1h + 16384;
+  unsigned char *y1h = H1_OUT ? h1_hi : t1h, *y1l = H1_OUT ? h1_lo : t1l;
+  const uint32_t a_y1h = H1_OUT ? a_h1_hi : sb + L.t1, a_y1l = H1_OUT ? a_h1_lo : sb + L.t1 + 16384u;
+  tile_put8(fh, fl, tid, 0, fin);
+  tile_put8(fh, fl, tid, 1, fin + 8);
+  ms.publish();
+  if (tid == 0) {
+    mma_chunks(tm + 0, sb + L.fin, sb + L.w0, 64, 2, false);
+    mma_chunks(tm + 0, sb + L.fin + 4096u, sb + L.w0, 64, 2, true);
+    ms.commit();
+  }
+  ms.wait();
+  m1a = m1b = m2a = m2b = 0u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[16];
+    tmem_ld16(tlane + (uint32_t)(q * 16), v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = q * 16 + i;
+      const bool on = v[i] > 0.f;
+      v[i] = on ? v[i] : 0.f;
+      if (k < 32) m1a |= on ? (1u << k) : 0u; else m1b |= on ? (1u << (k - 32)) : 0u;
+    }
+    tile_put8(y1h, y1l, tid, 2 * q, v);
+    tile_put8(y1h, y1l, tid, 2 * q + 1, v + 8);
+  }
+  ms.publish();
+  if (tid == 0) {
+    mma_chunks(tm + 64, a_y1h, sb + L.w1, 64, 8, false);
+    mma_chunks(tm + 64, a_y1l, sb + L.w1, 64, 8, true);
+    ms.commit();
+  }
+  ms.wait();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[16];
+    tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = q * 16 + i;
+      const bool on = v[i] > 0.f;
+      v[i] = on ? v[i] : 0.f;
+      if (k < 32) m2a |= on ? (1u << k) : 0u; else m2b |= on ? (1u << (k - 32)) : 0u;
+    }
+    tile_put8(t1h, t1l, tid, 2 * q, v);
+    tile_put8(t1h, t1l, tid, 2 * q + 1, v + 8);
+  }
+  ms.publish();
+  if (tid == 0) {
+    mma_chunks(tm + 0, sb + L.t1, sb + L.w2, 16, 8, false);
+    mma_chunks(tm + 0, sb + L.t1 + 16384u, sb + L.w2, 16, 8, true);
+    ms.commit();
+  }
+  ms.wait();
+  float o[16];
+  tmem_ld16(tlane, o);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) flow[k] = o[k];
+}
+}  // namespace l4dtc
+
+// -------------------------------------------------------------------------------------------
+// forward 1/2 with the flow MLP on tensor cores: thread == sample, tiles of 128 consecutive samples
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 3) k_fwd_gather_tc(const __grid_constant__ SplitArgs A) {
+  using namespace l4dtc;
+  extern __shared__ __align__(1024) unsigned char dsm[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const DevModel& M = A.M;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const FlowTcSmem L = flow_tc_smem();
+  const uint32_t sb = smem_u32(dsm);
+  float* xbuf = reinterpret_cast<float*>(dsm + L.total_fwd);     // [16][128] exchange columns of the feature gather
+  float* xb = xbuf + tid;
+  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&s_tmem, 128);
+  flow_copy_weights(dsm, L, M);
+  MmaSync ms{&s_bar, 0u};
+  ms.publish();
+  const uint32_t tm = s_tmem;
+  const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16);
+  const size_t P = A.sv.P;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  for (size_t base = (size_t)blockIdx.x * 128; base < P; base += (size_t)gridDim.x * 128) {
+    const size_t pp = base + tid;
+    const bool active = pp < P;
+    const size_t p = active ? pp : P - 1;
+    const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
+    const float zj = l4d_z(rs, A.ray_offset + ray, j);
+    const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
+    const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
+    const float z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
+    float fin[16];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      float e[8];
+      l4d_encode3_f8(M.gf, M.hf, l, x, y, z, e);
+      const float* b = A.F.flow_basis;
+      fin[2 * l] = ((b[0] * e[0] + b[1] * e[2]) + b[2] * e[4]) + b[3] * e[6];
+      fin[2 * l + 1] = ((b[0] * e[1] + b[1] * e[3]) + b[2] * e[5]) + b[3] * e[7];
+    }
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) A.sv.flow_in[(size_t)k * P + p] = fin[k];
+    }
+    float flow[8];
+    uint32_t a, b, c, d;
+    flow_forward_tc<false>(dsm, sb, L, ms, tm, tlane, fin, flow, a, b, c, d, nullptr, nullptr, 0u, 0u);
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) A.sv.flow[(size_t)k * P + p] = flow[k];
+      FeatSink sink;
+      sink.feat = A.sv.feat; sink.P = P; sink.p = p; sink.dense = nullptr;
+      float dummy[L4D_H];
+      l4d_gather_features<false>(M, A.F, x, y, z, flow, xb, 128, sink, dummy);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 128);
+}
+
+// -------------------------------------------------------------------------------------------
+// backward 3/3 on tensor cores: flow MLP backprop + weight gradients, then the flow-grid reductions
+// TMEM (256 cols): [0,64) [64,128) work, [128,144) dW2^T, [144,160) dW0, [192,256) dW1^T
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ SplitArgs A) {
+  using namespace l4dtc;
+  extern __shared__ __align__(1024) unsigned char dsm[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_w[32];
+  const DevModel& M = A.M;
+  const DevGrads& G = A.G;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const FlowTcSmem L = flow_tc_smem();
+  const uint32_t sb = smem_u32(dsm);
+  unsigned char *t2h = dsm + L.t2, *t2l = t2h + 16384, *t3h = dsm + L.t3, *t3l = t3h + 16384;
+  unsigned char *o16h = dsm + L.do16, *o16l = o16h + 4096;
+  const uint32_t aFinH = sb + L.fin, aFinL = aFinH + 4096u;
+  const uint32_t aT1h = sb + L.t1, aT1l = aT1h + 16384u, aT2h = sb + L.t2, aT2l = aT2h + 16384u, aT3h = sb + L.t3, aT3l = aT3h + 16384u;
+  const uint32_t aO16h = sb + L.do16, aO16l = aO16h + 4096u;
+  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&s_tmem, 256);
+  flow_copy_weights(dsm, L, M);
+  MmaSync ms{&s_bar, 0u};
+  ms.publish();
+  const uint32_t tm = s_tmem;
+  const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16);
+  const int row64 = warp * 16 + lane;
+  const bool has64 = lane < 16;
+  const size_t P = A.sv.P;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  for (size_t base = (size_t)blockIdx.x * 128; base < P; base += (size_t)gridDim.x * 128) {
+    const size_t pp = base + tid;
+    const bool active = pp < P;
+    const size_t p = active ? pp : P - 1;
+    float fin[16], g[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) fin[k] = active ? __ldg(A.sv.flow_in + (size_t)k * P + p) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) g[k] = (active && k < 6) ? __ldg(A.sv.dflow + (size_t)k * P + p) : 0.f;
+    float am = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) am = fmaxf(am, fabsf(g[k]));
+    am = block_amax128(am, s_w);
+    if (am == 0.f) continue;                       // no gradient reaches the flow field from this tile
+    // forward recompute: relu(layer 1) -> T2, relu(layer 2) -> T1, relu patterns
+    float flow[8];
+    uint32_t m1a, m1b, m2a, m2b;
+    flow_forward_tc<true>(dsm, sb, L, ms, tm, tlane, fin, flow, m1a, m1b, m2a, m2b, t2h, t2l, aT2h, aT2l);
+    const float sc = pow2_factor(am);
+    float inv = 1.0f / sc;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) g[k] *= sc;
+    tile_put8(o16h, o16l, tid, 0, g);
+    tile_put8(o16h, o16l, tid, 1, g + 8);
+    ms.publish();
+    if (tid == 0) {
+      // dH2[128 x 64] = dO * W2 (W2 stored [k/8][16 rows][8]) ; dW2^T[64 x 16] = H2^T * dO
+      mma_prop(tm + 0, aO16h, 2, sb + L.w2, 16, 64, false);
+      mma_prop(tm + 0, aO16l, 2, sb + L.w2, 16, 64, true);
+      mma_tt(tm + 128, aT1h, 64, aO16h, 16, false);
+      mma_tt(tm + 128, aT1l, 64, aO16h, 16, true);
+      mma_tt(tm + 128, aT1h, 64, aO16l, 16, true);
+      ms.commit();
+    }
+    ms.wait();
+    {
+      float v[16];
+      tmem_ld16(tlane + 128u, v);
+      if (has64) {
+#pragma unroll
+        for (int o = 0; o < 6; ++o) atomicAdd(G.flo_w2 + (size_t)o * 64 + row64, v[o] * inv);
+      }
+    }
+    float cs2;
+    {   // dH2 * relu2, re-scaled -> T3
+      float a2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[16];
+        tmem_ld16(tlane + (uint32_t)(q * 16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (l4d_bit(m2a, m2b, q * 16 + i)) a2 = fmaxf(a2, fabsf(v[i]));
+      }
+      a2 = block_amax128(a2, s_w);
+      const float r = a2 > 0.f ? pow2_factor(a2) : 1.0f;
+      cs2 = sc * r;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[16];
+        tmem_ld16(tlane + (uint32_t)(q * 16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = l4d_bit(m2a, m2b, q * 16 + i) ? v[i] * r : 0.f;
+        tile_put8(t3h, t3l, tid, 2 * q, v);
+        tile_put8(t3h, t3l, tid, 2 * q + 1, v + 8);
+      }
+    }
+    inv = 1.0f / cs2;
+    ms.publish();
+    if (tid == 0) {
+      // dH1[128 x 64] = dH2 * W1 ; dW1^T[64 x 64] = H1^T * dH2
+      mma_prop(tm + 64, aT3h, 8, sb + L.w1, 64, 64, false);
+      mma_prop(tm + 64, aT3l, 8, sb + L.w1, 64, 64, true);
+      mma_tt(tm + 192, aT2h, 64, aT3h, 64, false);
+      mma_tt(tm + 192, aT2l, 64, aT3h, 64, true);
+      mma_tt(tm + 192, aT2h, 64, aT3l, 64, true);
+      ms.commit();
+    }
+    ms.wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[16];
+      tmem_ld16(tlane + 192u + (uint32_t)(q * 16), v);
+      if (has64) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(G.flo_w1t + (size_t)row64 * 64 + q * 16 + i, v[i] * inv);
+      }
+    }
+    float cs3;
+    {   // dH1 * relu1, re-scaled -> T1 (H2 is dead)
+      unsigned char *t1h = dsm + L.t1, *t1l = t1h + 16384;
+      float a3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[16];
+        tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (l4d_bit(m1a, m1b, q * 16 + i)) a3 = fmaxf(a3, fabsf(v[i]));
+      }
+      a3 = block_amax128(a3, s_w);
+      const float r = a3 > 0.f ? pow2_factor(a3) : 1.0f;
+      cs3 = cs2 * r;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[16];
+        tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = l4d_bit(m1a, m1b, q * 16 + i) ? v[i] * r : 0.f;
+        tile_put8(t1h, t1l, tid, 2 * q, v);
+        tile_put8(t1h, t1l, tid, 2 * q + 1, v + 8);
+      }
+    }
+    inv = 1.0f / cs3;
+    ms.publish();
+    if (tid == 0) {
+      // dFin[128 x 16] = dH1 * W0 ; dW0[64 x 16] = dH1^T * Fin
+      mma_prop(tm + 0, aT1h, 8, sb + L.w0, 64, 16, false);
+      mma_prop(tm + 0, aT1l, 8, sb + L.w0, 64, 16, true);
+      mma_tt(tm + 144, aT1h, 64, aFinH, 16, false);
+      mma_tt(tm + 144, aT1l, 64, aFinH, 16, true);
+      mma_tt(tm + 144, aT1h, 64, aFinL, 16, true);
+      ms.commit();
+    }
+    ms.wait();
+    float dfin[16];
+    tmem_ld16(tlane, dfin);
+    {
+      float v[16];
+      tmem_ld16(tlane + 144u, v);
+      if (has64) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(G.flo_w0t + (size_t)i * 64 + row64, v[i] * inv);
+      }
+    }
+    if (active) {
+      // flow-grid reductions: feature (l, 2i+c) gets basis[i] * dFin[2l+c]
+      const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
+      const float zj = l4d_z(rs, A.ray_offset + ray, j);
+      const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
+      const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
+      const float z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
+      const float* b = A.F.flow_basis;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const float d0 = dfin[2 * l] * inv, d1 = dfin[2 * l + 1] * inv;
+        uint32_t idx[8]; float w[8];
+        l4d_corners3(M.gf, l, x, y, z, idx, w);
+        float* gb = G.hf + (size_t)M.gf.offset[l] * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float* q = gb + (size_t)idx[c] * 8;
+          l4d_red4(q, w[c] * b[0] * d0, w[c] * b[0] * d1, w[c] * b[1] * d0, w[c] * b[1] * d1);
+          l4d_red4(q + 4, w[c] * b[2] * d0, w[c] * b[2] * d1, w[c] * b[3] * d0, w[c] * b[3] * d1);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 256);
+}

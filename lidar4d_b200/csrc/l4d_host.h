@@ -15,7 +15,7 @@ struct StagedLayout {
   size_t sig_w1t, sig_w2t, sig_w2;
   size_t att_w1t[2], att_w2t[2], att_w2[2], att_w3[2];
   size_t flo_w0t, flo_w1t, flo_w1, flo_w2t, flo_w2;
-  size_t tc_sig_w1, tc_sig_w2, tc_att_w1g, tc_att_w2[2], tc_att_w1g_net[2];
+  size_t tc_sig_w1, tc_sig_w2, tc_att_w1g, tc_att_w2[2], tc_att_w1g_net[2], tc_flo_w0, tc_flo_w1, tc_flo_w2;
   size_t total;
 };
 struct GradWorkLayout {
@@ -69,6 +69,7 @@ static inline StagedLayout staged_layout(const L4DConfig* c) {
   L.tc_att_w1g = take(16 * 128 * 2);
   for (int n = 0; n < 2; ++n) L.tc_att_w2[n] = take(64 * 64 * 2);
   for (int n = 0; n < 2; ++n) L.tc_att_w1g_net[n] = take(16 * 64 * 2);
+  L.tc_flo_w0 = take(16 * 64 * 2); L.tc_flo_w1 = take(64 * 64 * 2); L.tc_flo_w2 = take(64 * 16 * 2);
   L.total = o;
   return L;
 }
@@ -160,6 +161,7 @@ static inline void build_model(const L4DConfig* c, const void* staged, DevModel&
   M.tc_sig_w1 = Hh(L.tc_sig_w1); M.tc_sig_w2 = Hh(L.tc_sig_w2); M.tc_att_w1g = Hh(L.tc_att_w1g);
   M.tc_att_w2[0] = Hh(L.tc_att_w2[0]); M.tc_att_w2[1] = Hh(L.tc_att_w2[1]);
   M.tc_att_w1g_net[0] = Hh(L.tc_att_w1g_net[0]); M.tc_att_w1g_net[1] = Hh(L.tc_att_w1g_net[1]);
+  M.tc_flo_w0 = Hh(L.tc_flo_w0); M.tc_flo_w1 = Hh(L.tc_flo_w1); M.tc_flo_w2 = Hh(L.tc_flo_w2);
   M.mlp_fp16 = c->mlp_fp16;
   M.sigma_in_dim = c->sigma_in_dim; M.sigma_in_pad = c->sigma_in_pad;
   M.attr_in_dim = c->attr_in_dim; M.attr_in_pad = c->attr_in_pad;

@@ -187,6 +187,10 @@ extern "C" int l4d_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, 
     k_pack_umma<<<nblk(64 * 64), 256, 0, st>>>(att[n] + 64 * ap, 64, 64, 0, 64, H(L.tc_att_w2[n]), 64, 0);
     k_pack_umma<<<nblk(64 * 16), 256, 0, st>>>(att[n], ap, 64, L4D_ENC, 16, H(L.tc_att_w1g_net[n]), 64, 0);
   }
+  k_pack_umma<<<nblk(64 * 16), 256, 0, st>>>(m->flow_mlp[0], 16, 64, 0, 16, H(L.tc_flo_w0), 64, 0);
+  k_pack_umma<<<nblk(64 * 64), 256, 0, st>>>(m->flow_mlp[1], 64, 64, 0, 64, H(L.tc_flo_w1), 64, 0);
+  cudaMemsetAsync(b + L.tc_flo_w2, 0, 64 * 16 * 2, st);
+  k_pack_umma<<<nblk(6 * 64), 256, 0, st>>>(m->flow_mlp[2], 64, 6, 0, 64, H(L.tc_flo_w2), 16, 0);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -835,7 +839,13 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
   A.depth = depth; A.image = image; A.wsum = wsum; A.weights = weights; A.zvals = zvals;
   A.train = 1u;
   const size_t P = (size_t)rays->n_rays * rays->n_steps;
-  {
+  if (cfg->mlp_fp16) {
+    const size_t smem = flow_tc_smem().total_fwd + 16 * 128 * sizeof(float) + 1024;
+    int grid;
+    rc = grid_for(k_fwd_gather_tc, 128, smem, (uint32_t)((P + 127) / 128), grid);
+    if (rc != L4D_OK) return rc;
+    k_fwd_gather_tc<<<grid, 128, smem, st>>>(A);
+  } else {
     const size_t smem = 64 * L4D_NT * sizeof(float);
     int grid;
     rc = grid_for(k_fwd_gather<L4D_NT>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
@@ -905,11 +915,19 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
       k_bwd_scatter<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
     }
     if (frame->has_fwd || frame->has_bwd) {     // with no neighbour frame nothing reaches the flow field
-      const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD) * sizeof(float);
-      int grid;
-      rc = grid_for(k_bwd_flow<L4D_NT>, L4D_NT, smem, tiles, grid);
-      if (rc != L4D_OK) return rc;
-      k_bwd_flow<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+      if (cfg->mlp_fp16) {
+        const size_t smem = flow_tc_smem().total + 1024;
+        int grid;
+        rc = grid_for(k_bwd_flow_tc, 128, smem, tiles, grid);
+        if (rc != L4D_OK) return rc;
+        k_bwd_flow_tc<<<grid, 128, smem, st>>>(A);
+      } else {
+        const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD) * sizeof(float);
+        int grid;
+        rc = grid_for(k_bwd_flow<L4D_NT>, L4D_NT, smem, tiles, grid);
+        if (rc != L4D_OK) return rc;
+        k_bwd_flow<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+      }
     }
     L4D_CUDA(cudaGetLastError());
     return L4D_OK;

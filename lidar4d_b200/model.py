@@ -179,7 +179,7 @@ class _Engine:
         with torch.cuda.device(self.device()):
             rc = lib.l4d_stage_params(C.byref(self.ccfg), C.byref(tab), self.staged.data_ptr(), nbytes, self.stream())
         _capi.check(lib, rc, "l4d_stage_params")
-        self.n_launches += 2 + 3 * self.cfg.time_resolution + 6 * self.cfg.n_levels_plane + 16 + 8 + (1 if self.mlp_fp16 else 0)
+        self.n_launches += 2 + 3 * self.cfg.time_resolution + 6 * self.cfg.n_levels_plane + 16 + 12 + (1 if self.mlp_fp16 else 0)
         self._stamp = stamp
 
     # ---- gradient arena -------------------------------------------------------
