@@ -71,6 +71,24 @@ def randomize(model, seed=0):
                 p.add_((torch.randn(p.shape, generator=g) * 0.1).to(p.device))
 
 
+def kernel_bytes(cfg):
+    """Algorithmic bytes per sample of every kernel of the pipeline."""
+    L, D = cfg.n_levels_hash, cfg.sigma_in_dim
+    planes = 4 * 3 * 4 * 32
+    gather = L * 8 * 8 + 3 * (3 * 2 * L * 4 * 8) + 8 * 8 * 16 + planes * 4
+    fwd, bwd = algorithmic_bytes(cfg)
+    exch = 4 * (D + 16 + 6)
+    return {
+        "forward": fwd, "backward": bwd, "k_render_fwd": fwd, "k_render_bwd": bwd,
+        "k_fwd_gather": gather + exch,                                     # table/plane gathers + feature / flow planes written
+        "k_fwd_flow": 8 * 8 * 16 + 4 * 22,                                 # flow-grid gather + flow-in / flow planes written
+        "k_fwd_dense": 4 * D + 12,                                          # features read, sigma/attr saved
+        "k_bwd_dense": 2 * 4 * D + 4 * D + 12,                              # features read twice, dfeat written
+        "k_bwd_scatter": 2 * (L * 8 * 16 + 3 * 2 * L * 4 * 16 + 4 * planes) + 4 * planes + 4 * D + 48,
+        "k_bwd_flow": 2 * (8 * 8 * 32) + 4 * 22,
+    }
+
+
 def algorithmic_bytes(cfg):
     """Per-sample algorithmic bytes (restated for this configuration in DESIGN.md)."""
     L = cfg.n_levels_hash
@@ -344,35 +362,34 @@ def run_b200(args):
     step(0, True)                                  # warm the e2e path (pinned copies)
     ms_e2e, _ = timed(True, args.steps, args.warmup)
 
-    # ---- per-kernel durations for the roofline (CUDA events on the launching stream) ----
-    eng = model._engine
-    eng.timing = {"fwd": [], "bwd": []}
-    for i in range(2):
-        step(args.warmup + i, False)
+    # ---- per-kernel durations for the roofline: CUDA events recorded by the library on the launch stream ----
+    from lidar4d_b200 import _capi
     torch.cuda.synchronize()
-    t_f = [a.elapsed_time(b) for a, b in eng.timing["fwd"]]
-    t_b = [a.elapsed_time(b) for a, b in eng.timing["bwd"]]
-    eng.timing = None
+    ktimes = _capi.profile_kernels(lambda: [step(args.warmup + i, False) for i in range(2)])
+    torch.cuda.synchronize()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    fwd_b, bwd_b = algorithmic_bytes(model.cfg)
     peak, peak_src = peaks()
     samples_per_launch = min(rb, n_rays) * S_STEPS
+    kbytes = kernel_bytes(model.cfg)
     kern = {}
-    for name, ts, b in (("forward (k_fwd_gather+k_fwd_dense*)" if args.pipeline == "split" else "k_render_fwd", t_f, fwd_b), ("backward (k_bwd_dense+k_bwd_scatter+k_bwd_flow)" if args.pipeline == "split" else "k_render_bwd", t_b, bwd_b)):
-        if ts:
-            avg = float(np.mean(ts))
-            kern[name] = {"avg_ms": avg, "launches_timed": len(ts), "alg_bytes_per_sample": b,
-                          "achieved_gbs": b * samples_per_launch / (avg * 1e-3) / 1e9}
+    for name, ts in ktimes.items():
+        avg = float(np.mean(ts))
+        b = kbytes.get(name.replace("_tc", ""), None)
+        kern[name] = {"avg_ms": avg, "launches_timed": len(ts), "alg_bytes_per_sample": b,
+                      "achieved_gbs": (b * samples_per_launch / (avg * 1e-3) / 1e9) if b else None}
     dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
     roofline = None
     if dom:
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src, "kernels": kern,
-                    "note": "algorithmic bytes (DESIGN.md); tables fit the 126 MB L2 so dram bytes (profiles/) are lower"}
+        ach = kern[dom]["achieved_gbs"]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src, "kernels": kern,
+                    "whole_forward_gbs": kbytes["forward"] * samples_per_launch / (sum(kern[k]["avg_ms"] for k in kern if "fwd" in k) * 1e-3) / 1e9,
+                    "whole_backward_gbs": kbytes["backward"] * samples_per_launch / (sum(kern[k]["avg_ms"] for k in kern if "bwd" in k) * 1e-3) / 1e9,
+                    "note": "algorithmic bytes per kernel (DESIGN.md 4.3); the fp16 tables fit the 126 MB L2, so dram bytes (profiles/) are lower"}
     total_rays = n_rays * world * args.steps
     value = total_rays / (ms * 1e-3)
     line = {
@@ -386,7 +403,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": n_rays * 3 * 4 + 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
-    log(f"e2e {ms_e2e / args.steps:.1f} ms/step; kernels {kern}")
+    log(f"e2e {ms_e2e / args.steps:.1f} ms/step; kernels " + ", ".join(f"{k} {v['avg_ms']:.2f} ms" for k, v in kern.items()))
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_subprocess(args)
     print(json.dumps(line), flush=True)

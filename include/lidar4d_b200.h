@@ -196,6 +196,12 @@ int    l4d_density_forward(const L4DConfig* cfg, const void* staged, const L4DFr
                            const float* x, uint32_t n, float* sigma, float* geo,
                            float* features_or_null, float* flow_or_null, void* stream);
 
+/* --- profiling aid: while started, CUDA events are recorded on the launch stream around every kernel of
+ *     l4d_render_forward / l4d_render_backward.  l4d_profile_stop returns the number of (kernel name, ms)
+ *     pairs written (static strings), or a negative error code.  Not thread-safe. --------------------------- */
+int    l4d_profile_start(void);
+int    l4d_profile_stop(const char** names, float* ms, int cap);
+
 /* tcgen05/TMEM self-test of the MLP engine's building blocks: C[128,N] = A[128,K] * B[N,K]^T,
  * fp16 operands, fp32 accumulate (N%16==0 in [16,256], K%16==0 in [16,512]). */
 int    l4d_tc_selftest(const void* A_half, const void* B_half, float* C, uint32_t N, uint32_t K, void* stream);

@@ -138,7 +138,7 @@ LIB_NAME = "liblidar4d_b200.so"
 EXPORTS = [
     "l4d_abi_version", "l4d_last_error", "l4d_staged_bytes", "l4d_stage_params", "l4d_saved_bytes",
     "l4d_render_forward", "l4d_grad_work_bytes", "l4d_render_backward", "l4d_unstage_grads",
-    "l4d_flow_forward", "l4d_flow_backward", "l4d_hash_indices", "l4d_density_forward", "l4d_tc_selftest", "l4d_tc_selftest2",
+    "l4d_flow_forward", "l4d_flow_backward", "l4d_hash_indices", "l4d_density_forward", "l4d_tc_selftest", "l4d_tc_selftest2", "l4d_profile_start", "l4d_profile_stop",
 ]
 
 
@@ -175,6 +175,10 @@ def declare(lib, prefix: str = "l4d_", host_sim: bool = False):
         lib.l4d_tc_selftest.restype = C.c_int
         lib.l4d_tc_selftest2.argtypes = [V, V, V, U32, U32, U32, U32, U32, V]
         lib.l4d_tc_selftest2.restype = C.c_int
+        lib.l4d_profile_start.argtypes = []
+        lib.l4d_profile_start.restype = C.c_int
+        lib.l4d_profile_stop.argtypes = [P(C.c_char_p), P(C.c_float), C.c_int]
+        lib.l4d_profile_stop.restype = C.c_int
     else:
         f("stage_params").argtypes = [P(L4DConfig), P(L4DMasterParams), V]
         f("render_forward").argtypes = [P(L4DConfig), V, P(L4DFrame), P(L4DRays), V, V, V, V, V, V]
@@ -250,3 +254,21 @@ def fill_pointer_table(table, cfg: FieldConfig, ptr_of):
     table.intensity_net = ptr_of("intensity_net.params")
     table.raydrop_net = ptr_of("raydrop_net.params")
     return table
+
+
+def profile_kernels(fn, cap: int = 256):
+    """Run fn() with per-kernel CUDA-event timing enabled; returns {kernel name: [ms, ...]}."""
+    lib = load_library()
+    lib.l4d_profile_start()
+    try:
+        fn()
+    finally:
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        n = lib.l4d_profile_stop(names, ms, cap)
+    if n < 0:
+        raise RuntimeError(lib.l4d_last_error().decode())
+    out = {}
+    for i in range(n):
+        out.setdefault(names[i].decode(), []).append(float(ms[i]))
+    return out

@@ -936,9 +936,12 @@ __device__ __forceinline__ void flow_forward_tc(unsigned char* dsm, uint32_t sb,
 }  // namespace l4dtc
 
 // -------------------------------------------------------------------------------------------
-// forward 1/2 with the flow MLP on tensor cores: thread == sample, tiles of 128 consecutive samples
+// forward 0/2: flow field on tensor cores (flow-grid gather + 16->64->64->6 MLP), tiles of 128 consecutive
+// samples; writes the flow-MLP inputs and the flow.  Kept apart from the feature gather on purpose: the MMA
+// round trips need block-wide barriers, and barriers around the long, irregular feature gathers stall warps
+// that would otherwise run free (measured: fusing them doubled the forward at L=16).
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 3) k_fwd_gather_tc(const __grid_constant__ SplitArgs A) {
+__global__ void __launch_bounds__(128, 4) k_fwd_flow_tc(const __grid_constant__ SplitArgs A) {
   using namespace l4dtc;
   extern __shared__ __align__(1024) unsigned char dsm[];
   __shared__ __align__(8) uint64_t s_bar;
@@ -947,8 +950,6 @@ __global__ void __launch_bounds__(128, 3) k_fwd_gather_tc(const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5;
   const FlowTcSmem L = flow_tc_smem();
   const uint32_t sb = smem_u32(dsm);
-  float* xbuf = reinterpret_cast<float*>(dsm + L.total_fwd);     // [16][128] exchange columns of the feature gather
-  float* xb = xbuf + tid;
   if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&s_tmem, 128);
   flow_copy_weights(dsm, L, M);
@@ -986,10 +987,6 @@ __global__ void __launch_bounds__(128, 3) k_fwd_gather_tc(const __grid_constant_
     if (active) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) A.sv.flow[(size_t)k * P + p] = flow[k];
-      FeatSink sink;
-      sink.feat = A.sv.feat; sink.P = P; sink.p = p; sink.dense = nullptr;
-      float dummy[L4D_H];
-      l4d_gather_features<false>(M, A.F, x, y, z, flow, xb, 128, sink, dummy);
     }
     tc_fence_before();
     __syncthreads();

@@ -27,6 +27,39 @@ int l4d_fail(int code, const char* fmt, const char* a, const char* b) {
     if (e__ != cudaSuccess) return l4d_fail(L4D_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
   } while (0)
 
+// -----------------------------------------------------------------------------
+// optional per-kernel timing (profiling aid, not thread-safe): CUDA events recorded on the launch
+// stream around every kernel of the render pipeline while enabled
+// -----------------------------------------------------------------------------
+#define L4D_PROF_MAX 256
+static bool g_prof = false;
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_ev[L4D_PROF_MAX];
+static const char* g_prof_name[L4D_PROF_MAX];
+static void prof_mark(cudaStream_t st, const char* name) {
+  if (!g_prof || g_prof_n >= L4D_PROF_MAX) return;
+  if (!g_prof_ev[g_prof_n]) cudaEventCreate(&g_prof_ev[g_prof_n]);
+  cudaEventRecord(g_prof_ev[g_prof_n], st);
+  g_prof_name[g_prof_n++] = name;
+}
+extern "C" int l4d_profile_start(void) { g_prof = true; g_prof_n = 0; return L4D_OK; }
+// stops recording, synchronises the recorded events and writes up to `cap` (name, milliseconds) pairs: the time
+// from the previous mark to the mark called `name`; marks called "begin" open a new call and are skipped
+extern "C" int l4d_profile_stop(const char** names, float* ms, int cap) {
+  g_prof = false;
+  int n = 0;
+  for (int i = 1; i < g_prof_n && n < cap; ++i) {
+    if (!strcmp(g_prof_name[i], "begin")) continue;
+    if (cudaEventSynchronize(g_prof_ev[i]) != cudaSuccess) return l4d_fail(L4D_ECUDA, "cudaEventSynchronize failed");
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof_ev[i - 1], g_prof_ev[i]) != cudaSuccess) return l4d_fail(L4D_ECUDA, "cudaEventElapsedTime failed");
+    names[n] = g_prof_name[i];
+    ms[n++] = t;
+  }
+  g_prof_n = 0;
+  return n;
+}
+
 extern "C" int l4d_abi_version(void) { return L4D_ABI_VERSION; }
 extern "C" const char* l4d_last_error(void) { return g_err; }
 
@@ -815,6 +848,7 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
   if (saved && saved_bytes < saved_layout(cfg, rays->n_rays, rays->n_steps).total) return l4d_fail(L4D_ESIZE, "saved buffer too small");
   const bool fused = (rays->reserved & L4D_FLAG_FUSED) || !saved;
   cudaStream_t st = (cudaStream_t)stream;
+  prof_mark(st, "begin");
   if (fused) {
     FwdArgs A;
     memset(&A, 0, sizeof(A));
@@ -831,6 +865,7 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
     rc = grid_for(k_render_fwd<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
     if (rc != L4D_OK) return rc;
     k_render_fwd<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+    prof_mark(st, "k_render_fwd");
     L4D_CUDA(cudaGetLastError());
     return L4D_OK;
   }
@@ -840,17 +875,27 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
   A.train = 1u;
   const size_t P = (size_t)rays->n_rays * rays->n_steps;
   if (cfg->mlp_fp16) {
-    const size_t smem = flow_tc_smem().total_fwd + 16 * 128 * sizeof(float) + 1024;
+    {
+      const size_t smem = flow_tc_smem().total_fwd + 1024;
+      int grid;
+      rc = grid_for(k_fwd_flow_tc, 128, smem, (uint32_t)((P + 127) / 128), grid);
+      if (rc != L4D_OK) return rc;
+      k_fwd_flow_tc<<<grid, 128, smem, st>>>(A);
+      prof_mark(st, "k_fwd_flow_tc");
+    }
+    const size_t smem = 16 * L4D_NT * sizeof(float);
     int grid;
-    rc = grid_for(k_fwd_gather_tc, 128, smem, (uint32_t)((P + 127) / 128), grid);
+    rc = grid_for(k_fwd_gather<L4D_NT, true>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
     if (rc != L4D_OK) return rc;
-    k_fwd_gather_tc<<<grid, 128, smem, st>>>(A);
+    k_fwd_gather<L4D_NT, true><<<grid, L4D_NT, smem, st>>>(A);
+    prof_mark(st, "k_fwd_gather");
   } else {
     const size_t smem = 64 * L4D_NT * sizeof(float);
     int grid;
-    rc = grid_for(k_fwd_gather<L4D_NT>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
+    rc = grid_for(k_fwd_gather<L4D_NT, false>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
     if (rc != L4D_OK) return rc;
-    k_fwd_gather<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+    k_fwd_gather<L4D_NT, false><<<grid, L4D_NT, smem, st>>>(A);
+    prof_mark(st, "k_fwd_gather");
   }
   if (cfg->mlp_fp16) {
     const size_t smem = dense_fwd_smem(cfg->sigma_in_pad).total + 1024;
@@ -858,12 +903,14 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
     rc = grid_for(k_fwd_dense_tc, 128, smem, rays->n_rays, grid);
     if (rc != L4D_OK) return rc;
     k_fwd_dense_tc<<<grid, 128, smem, st>>>(A);
+    prof_mark(st, "k_fwd_dense_tc");
   } else {
     const size_t smem = (64 * L4D_NT + 80 + 128 + 32) * sizeof(float);
     int grid;
     rc = grid_for(k_fwd_dense<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
     if (rc != L4D_OK) return rc;
     k_fwd_dense<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+    prof_mark(st, "k_fwd_dense");
   }
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
@@ -886,6 +933,7 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
       if (!grads->hash_dynamic[p][s]) return l4d_fail(L4D_EINVAL, "null hash_dynamic gradient buffer");
   if (rays->n_rays == 0) return L4D_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  prof_mark(st, "begin");
   if (!(rays->reserved & L4D_FLAG_FUSED)) {
     SplitArgs A;
     fill_split(A, cfg, staged, frame, rays, const_cast<void*>(saved));
@@ -900,6 +948,7 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
       rc = grid_for(k_bwd_dense_tc, 128, smem, rays->n_rays, grid);
       if (rc != L4D_OK) return rc;
       k_bwd_dense_tc<<<grid, 128, smem, st>>>(A);
+      prof_mark(st, "k_bwd_dense_tc");
     } else {
       const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD + 80 + 128 + 128 + 32 + L4D_MAX_TILES) * sizeof(float);
       int grid;
@@ -907,12 +956,14 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
       if (rc != L4D_OK) return rc;
       if (grid > L4D_BWD_SCRATCH_CTAS) grid = L4D_BWD_SCRATCH_CTAS;
       k_bwd_dense<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+      prof_mark(st, "k_bwd_dense");
     }
     {
       int grid;
       rc = grid_for(k_bwd_scatter<L4D_NT>, L4D_NT, 0, tiles, grid);
       if (rc != L4D_OK) return rc;
       k_bwd_scatter<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
+      prof_mark(st, "k_bwd_scatter");
     }
     if (frame->has_fwd || frame->has_bwd) {     // with no neighbour frame nothing reaches the flow field
       if (cfg->mlp_fp16) {
@@ -921,12 +972,14 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
         rc = grid_for(k_bwd_flow_tc, 128, smem, tiles, grid);
         if (rc != L4D_OK) return rc;
         k_bwd_flow_tc<<<grid, 128, smem, st>>>(A);
+        prof_mark(st, "k_bwd_flow_tc");
       } else {
         const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD) * sizeof(float);
         int grid;
         rc = grid_for(k_bwd_flow<L4D_NT>, L4D_NT, smem, tiles, grid);
         if (rc != L4D_OK) return rc;
         k_bwd_flow<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+        prof_mark(st, "k_bwd_flow");
       }
     }
     L4D_CUDA(cudaGetLastError());
@@ -948,6 +1001,7 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
   if (rc != L4D_OK) return rc;
   if (grid > L4D_BWD_SCRATCH_CTAS) grid = L4D_BWD_SCRATCH_CTAS;
   k_render_bwd<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+  prof_mark(st, "k_render_bwd");
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }

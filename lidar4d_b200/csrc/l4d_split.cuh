@@ -30,7 +30,8 @@ struct SplitArgs {
 // -------------------------------------------------------------------------------------------
 // forward 1/2: encoders.  thread == sample; writes features, flow-MLP inputs and flow.
 // -------------------------------------------------------------------------------------------
-template <int NT>
+// FLOW_GIVEN: the flow was already written by k_fwd_flow_tc; then this kernel has no MLP at all
+template <int NT, bool FLOW_GIVEN>
 __global__ void __launch_bounds__(NT, 4) k_fwd_gather(const __grid_constant__ SplitArgs A) {
   extern __shared__ __align__(16) float smem[];
   float* xb = smem + threadIdx.x;          // exchange column for the flow MLP, stride NT
@@ -46,13 +47,17 @@ __global__ void __launch_bounds__(NT, 4) k_fwd_gather(const __grid_constant__ Sp
     const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
     const float z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
     float flow[8];
-    {
+    if (FLOW_GIVEN) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) flow[k] = __ldg(A.sv.flow + (size_t)k * P + p);
+      flow[6] = flow[7] = 0.f;
+    } else {
       l4d_flow_inputs(M, A.F.flow_basis, x, y, z, xb, NT, A.sv.flow_in + p, P);
       uint32_t a, b, c, d;
       l4d_flow_mlp(M, xb, NT, flow, a, b, c, d);
-    }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) A.sv.flow[(size_t)k * P + p] = flow[k];
+      for (int k = 0; k < 6; ++k) A.sv.flow[(size_t)k * P + p] = flow[k];
+    }
     FeatSink sink;
     sink.feat = A.sv.feat; sink.P = P; sink.p = p; sink.dense = nullptr;
     float dummy[L4D_H];

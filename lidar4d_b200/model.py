@@ -236,7 +236,7 @@ class _RenderFn(torch.autograd.Function):
                 saved.data_ptr() if saved is not None else None, nsaved, eng.stream())
             if ev: ev[1].record()
         _capi.check(lib, rc, "l4d_render_forward")
-        eng.n_launches += 1 if fused else 2
+        eng.n_launches += 1 if fused else (3 if eng.mlp_fp16 else 2)
         ctx.eng, ctx.frame, ctx.rays_args = eng, frame, (N, S, int(bool(perturb)), int(seed), int(ray_offset))
         ctx.saved, ctx.nsaved = (saved, nsaved) if train else (None, 0)
         ctx.fused = fused
