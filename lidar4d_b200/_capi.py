@@ -143,7 +143,8 @@ EXPORTS = [
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
+    # L4D_LIB_PATH: developer override to A/B test differently compiled builds of the same library
+    return os.environ.get("L4D_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
 
 
 def declare(lib, prefix: str = "l4d_", host_sim: bool = False):

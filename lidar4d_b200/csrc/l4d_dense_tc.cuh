@@ -998,7 +998,7 @@ __global__ void __launch_bounds__(128, 4) k_fwd_flow_tc(const __grid_constant__ 
 }
 
 // -------------------------------------------------------------------------------------------
-// backward 3/3 on tensor cores: flow MLP backprop + weight gradients, then the flow-grid reductions
+// backward 3/4 on tensor cores: flow MLP backprop + weight gradients; dL/d(flow-MLP input) -> flow_in planes
 // TMEM (256 cols): [0,64) [64,128) work, [128,144) dW2^T, [144,160) dW0, [192,256) dW1^T
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ SplitArgs A) {
@@ -1041,7 +1041,13 @@ __global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ Spl
 #pragma unroll
     for (int k = 0; k < 6; ++k) am = fmaxf(am, fabsf(g[k]));
     am = block_amax128(am, s_w);
-    if (am == 0.f) continue;                       // no gradient reaches the flow field from this tile
+    if (am == 0.f) {                               // no gradient reaches the flow field from this tile
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) A.sv.flow_in[(size_t)k * P + p] = 0.f;
+      }
+      continue;
+    }
     // forward recompute: relu(layer 1) -> T2, relu(layer 2) -> T1, relu patterns
     float flow[8];
     uint32_t m1a, m1b, m2a, m2b;
@@ -1162,26 +1168,10 @@ __global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ Spl
       }
     }
     if (active) {
-      // flow-grid reductions: feature (l, 2i+c) gets basis[i] * dFin[2l+c]
-      const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
-      const float zj = l4d_z(rs, A.ray_offset + ray, j);
-      const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
-      const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
-      const float z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
-      const float* b = A.F.flow_basis;
+      // dL/d(flow-MLP input) replaces the saved input in place (same thread, same addresses); k_bwd_flowgrid
+      // turns it into flow-grid reductions at full occupancy
 #pragma unroll
-      for (int l = 0; l < 8; ++l) {
-        const float d0 = dfin[2 * l] * inv, d1 = dfin[2 * l + 1] * inv;
-        uint32_t idx[8]; float w[8];
-        l4d_corners3(M.gf, l, x, y, z, idx, w);
-        float* gb = G.hf + (size_t)M.gf.offset[l] * 8;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float* q = gb + (size_t)idx[c] * 8;
-          l4d_red4(q, w[c] * b[0] * d0, w[c] * b[0] * d1, w[c] * b[1] * d0, w[c] * b[1] * d1);
-          l4d_red4(q + 4, w[c] * b[2] * d0, w[c] * b[2] * d1, w[c] * b[3] * d0, w[c] * b[3] * d1);
-        }
-      }
+      for (int k = 0; k < 16; ++k) A.sv.flow_in[(size_t)k * P + p] = dfin[k] * inv;
     }
     tc_fence_before();
     __syncthreads();

@@ -808,14 +808,17 @@ static int check_rays(const L4DRays* r) {
   return L4D_OK;
 }
 
+// force_per_sm > 0 overrides the occupancy query: for kernels that allocate tensor memory the runtime reports one
+// CTA per SM although registers / shared memory / the 128 TMEM columns they actually allocate allow more
 template <typename K>
-static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid) {
+static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid, int force_per_sm = 0) {
   int per_sm = 0;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
   if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
   if (per_sm < 1) per_sm = 1;
+  if (force_per_sm > 0) per_sm = force_per_sm;
   long g = (long)per_sm * sm_count();
   if ((long)work < g) g = work;
   if (g < 1) g = 1;
@@ -878,7 +881,7 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
     {
       const size_t smem = flow_tc_smem().total_fwd + 1024;
       int grid;
-      rc = grid_for(k_fwd_flow_tc, 128, smem, (uint32_t)((P + 127) / 128), grid);
+      rc = grid_for(k_fwd_flow_tc, 128, smem, (uint32_t)((P + 127) / 128), grid, 4);
       if (rc != L4D_OK) return rc;
       k_fwd_flow_tc<<<grid, 128, smem, st>>>(A);
       prof_mark(st, "k_fwd_flow_tc");
@@ -973,6 +976,10 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
         if (rc != L4D_OK) return rc;
         k_bwd_flow_tc<<<grid, 128, smem, st>>>(A);
         prof_mark(st, "k_bwd_flow_tc");
+        rc = grid_for(k_bwd_flowgrid<L4D_NT>, L4D_NT, 0, tiles, grid);
+        if (rc != L4D_OK) return rc;
+        k_bwd_flowgrid<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
+        prof_mark(st, "k_bwd_flowgrid");
       } else {
         const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD) * sizeof(float);
         int grid;

@@ -271,6 +271,9 @@ __global__ void __launch_bounds__(NT) k_bwd_dense(const __grid_constant__ SplitA
 // -------------------------------------------------------------------------------------------
 // backward 2/3: scatter dL/dfeature through the encoders (vector REDs), thread == sample.
 // -------------------------------------------------------------------------------------------
+#ifndef L4D_SCATTER_MIN_CTAS
+#define L4D_SCATTER_MIN_CTAS 4
+#endif
 struct DfeatFromPlaneMasked {
   const float* base;
   size_t stride;
@@ -279,7 +282,7 @@ struct DfeatFromPlaneMasked {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 4) k_bwd_scatter(const __grid_constant__ SplitArgs A) {
+__global__ void __launch_bounds__(NT, L4D_SCATTER_MIN_CTAS) k_bwd_scatter(const __grid_constant__ SplitArgs A) {
   const DevModel& M = A.M;
   const size_t P = A.sv.P;
   const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
@@ -350,5 +353,58 @@ __global__ void __launch_bounds__(NT) k_bwd_flow(const __grid_constant__ SplitAr
     l4d_bw_flow_c(M, A.F, A.G, s, A.sv.flow_in + p, P, xb, NT, ta_row, tb_row);
     __syncthreads();
     tile_outer_accum<NT>(TA, TB, 16, A.G.flo_w0t);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// backward 4/4 (tensor-core path): flow-grid reductions from dL/d(flow-MLP input), thread == sample.
+// Feature (l, 2i+c) of a corner gets basis[i] * w_corner * dFin[2l+c].  The coarse levels (cells wider than
+// the span of a warp of consecutive samples) are summed per run of equal cells with segmented warp scans first.
+// -------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 4) k_bwd_flowgrid(const __grid_constant__ SplitArgs A) {
+  const DevModel& M = A.M;
+  const size_t P = A.sv.P;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  const float* b = A.F.flow_basis;
+  for (size_t base = (size_t)blockIdx.x * NT; base < P; base += (size_t)gridDim.x * NT) {
+    const size_t pp = base + threadIdx.x;
+    const bool active = pp < P;
+    const size_t p = active ? pp : P - 1;
+    const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
+    const float zj = l4d_z(rs, A.ray_offset + ray, j);
+    const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
+    const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
+    const float z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
+#pragma unroll 1
+    for (int l = 0; l < 8; ++l) {
+      const float d0 = active ? __ldg(A.sv.flow_in + (size_t)(2 * l) * P + p) : 0.f;
+      const float d1 = active ? __ldg(A.sv.flow_in + (size_t)(2 * l + 1) * P + p) : 0.f;
+      uint32_t idx[8]; float w[8];
+      l4d_corners3(M.gf, l, x, y, z, idx, w);
+      float* gb = A.G.hf + (size_t)M.gf.offset[l] * 8;
+      if (M.gf.res[l] <= 400u) {            // warp-uniform: aggregate runs of equal cells
+        uint32_t cx, cy, cz; float fx, fy, fz;
+        const float sc = M.gf.scale[l];
+        l4d_pos_fract(sc, x, cx, fx); l4d_pos_fract(sc, y, cy, fy); l4d_pos_fract(sc, z, cz, fz);
+        const WarpRuns r = l4d_warp_runs((int)(cx + M.gf.res[l] * (cy + M.gf.res[l] * cz)));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float s0 = l4d_seg_sum(w[c] * d0, r.dist), s1 = l4d_seg_sum(w[c] * d1, r.dist);
+          if (r.tail) {
+            float* q = gb + (size_t)idx[c] * 8;
+            l4d_red4(q, b[0] * s0, b[0] * s1, b[1] * s0, b[1] * s1);
+            l4d_red4(q + 4, b[2] * s0, b[2] * s1, b[3] * s0, b[3] * s1);
+          }
+        }
+      } else if (active) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float* q = gb + (size_t)idx[c] * 8;
+          l4d_red4(q, w[c] * b[0] * d0, w[c] * b[0] * d1, w[c] * b[1] * d0, w[c] * b[1] * d1);
+          l4d_red4(q + 4, w[c] * b[2] * d0, w[c] * b[2] * d1, w[c] * b[3] * d0, w[c] * b[3] * d1);
+        }
+      }
+    }
   }
 }
