@@ -829,6 +829,563 @@ __global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ Sp
   if (warp == 0) tmem_dealloc(tm, 512);
 }
 
+
+namespace l4dtc {
+// 256-thread CTA with two threads per row: warps 0-3 and 4-7 run the same 128-wide scans redundantly
+__device__ __forceinline__ float half_excl_prod(float v, float* s_w, float& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, base = warp & 4, wq = warp & 3;
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc *= t;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  float ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) ex = 1.f;
+  __syncthreads();
+  float pre = 1.f, tot = 1.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float t = s_w[base + w];
+    if (w < wq) pre *= t;
+    tot *= t;
+  }
+  total = tot;
+  __syncthreads();
+  return pre * ex;
+}
+__device__ __forceinline__ float half_excl_suffix_sum(float v, float* s_w, float& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, base = warp & 4, wq = warp & 3;
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_down_sync(0xffffffffu, inc, o);
+    if (lane + o < 32) inc += t;
+  }
+  if (lane == 0) s_w[warp] = inc;
+  float ex = __shfl_down_sync(0xffffffffu, inc, 1);
+  if (lane == 31) ex = 0.f;
+  __syncthreads();
+  float post = 0.f, tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float t = s_w[base + w];
+    if (w > wq) post += t;
+    tot += t;
+  }
+  total = tot;
+  __syncthreads();
+  return post + ex;
+}
+__device__ __forceinline__ float block_amax256(float v, float* s_w) {
+  v = fabsf(v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s_w[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) r = fmaxf(r, s_w[w]);
+  __syncthreads();
+  return r;
+}
+}  // namespace l4dtc
+
+// Same kernel with 256 threads: two threads per row split the columns of every epilogue (tcgen05.ld lets warps
+// w and w+4 address the same TMEM lane quadrant), which doubles the warps that hide latency (ncu on the
+// 128-thread version: 4 warps/SM, IPC 0.45, stalls on long_scoreboard / wait / instruction fetch).
+__global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ SplitArgs A) {
+  using namespace l4dtc;
+  extern __shared__ __align__(1024) unsigned char dsm[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const DevModel& M = A.M;
+  const DevGrads& G = A.G;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, half = tid >> 7, wq = warp & 3;     // two threads per row: `half` owns columns [32*half, 32*half+32) of every 64-wide block
+  const uint32_t in_pad = M.sigma_in_pad;
+  const DenseBwdSmem L = dense_bwd_smem(in_pad);
+  const uint32_t sb = smem_u32(dsm);
+  // tile views
+  unsigned char* xh = dsm + L.R;                 // X hi: 24 chunks
+  unsigned char* xl = dsm + L.R + 48 * 1024;     // X lo
+  unsigned char* t1h = dsm + L.R, *t1l = t1h + 16384;              // T1
+  unsigned char* t2h = dsm + L.R + 32768, *t2l = t2h + 16384;      // T2
+  unsigned char* t3h = dsm + L.R + 65536, *t3l = t3h + 16384;      // T3
+  unsigned char* hh = dsm + L.RH, *hl = hh + 16384;
+  unsigned char* g16h = dsm + L.g16, *g16l = g16h + 4096;
+  unsigned char* o16h = dsm + L.do16, *o16l = o16h + 4096;
+  unsigned char* o8h = dsm + L.do8, *o8l = o8h + 2048;
+  const uint32_t aXh = sb + L.R, aXl = aXh + 48 * 1024;
+  const uint32_t aT1h = sb + L.R, aT1l = aT1h + 16384, aT2h = aT1h + 32768, aT2l = aT2h + 16384, aT3h = aT1h + 65536, aT3l = aT3h + 16384;
+  const uint32_t aHh = sb + L.RH, aHl = aHh + 16384;
+  const uint32_t aG16h = sb + L.g16, aG16l = aG16h + 4096, aO16h = sb + L.do16, aO16l = aO16h + 4096, aO8h = sb + L.do8, aO8l = aO8h + 2048;
+  float* s_enc = reinterpret_cast<float*>(dsm + L.misc);
+  float* s_cdir = s_enc + 80;      // full per-ray first-layer term (as the forward uses it)
+  float* s_cdir2 = s_cdir + 128;   // same minus the first ones-row (the tile's column 15 carries that 1)
+  float* s_csum = s_cdir2 + 128;
+  float* s_w = s_csum + 128;
+  float* s_tstart = s_w + 32;
+  __shared__ float s_w3max[2];
+  __shared__ float s_part[256];
+
+  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&s_tmem, 512);
+  if (tid < 2) {
+    float m = 1.0f;
+    for (int k = 0; k < 64; ++k) m = fmaxf(m, fabsf(l4d_ld1(M.att_w3[tid] + k)));
+    s_w3max[tid] = m;
+  }
+  {
+    auto cp = [&](uint32_t off, const __half* src, uint32_t bytes) {
+      for (uint32_t i = tid * 16; i < bytes; i += 256 * 16)
+        *reinterpret_cast<uint4*>(dsm + off + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(src) + i));
+    };
+    cp(L.w1, M.tc_sig_w1, in_pad * 64 * 2);
+    cp(L.w2, M.tc_sig_w2, 64 * 16 * 2);
+    cp(L.wa1[0], M.tc_att_w1g_net[0], 16 * 64 * 2);
+    cp(L.wa1[1], M.tc_att_w1g_net[1], 16 * 64 * 2);
+    cp(L.wa2[0], M.tc_att_w2[0], 64 * 64 * 2);
+    cp(L.wa2[1], M.tc_att_w2[1], 64 * 64 * 2);
+  }
+  MmaSync ms{&s_bar, 0u};
+  ms.publish();
+  const uint32_t tm = s_tmem;
+  const uint32_t tlane = tm + ((uint32_t)(wq * 32) << 16);
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  const uint32_t S = A.S;
+  const int n_tiles = (int)((S + 127) / 128);
+  const float kk = M.active_sensor ? 2.0f : 1.0f;
+  const int n_xchunks = (int)in_pad / 8;
+  const int row64 = wq * 16 + lane;            // row held by this thread in an M=64 accumulator (lanes < 16)
+  const bool has64 = lane < 16;
+
+  // features of this thread's sample -> X tile (24 chunks, zero beyond in_pad)
+  auto load_x = [&](size_t p, bool valid) {
+    for (int c0 = 4 * half; c0 < 24; c0 += 8) {      // the two threads of a row interleave groups of 4 chunks
+      float v[4][8];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = (c0 + cc) * 8 + i;
+          v[cc][i] = (!valid || k >= (int)in_pad) ? 0.f : (k < (int)M.sigma_in_dim ? __ldg(A.sv.feat + (size_t)k * A.sv.P + p) : 1.0f);
+        }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tile_put8(xh, xl, row, c0 + cc, v[cc]);
+    }
+  };
+
+  for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
+    const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
+    const float gd = __ldg(A.g_depth + ray), gi0 = __ldg(A.g_image + 2 * ray), gi1 = __ldg(A.g_image + 2 * ray + 1);
+    const float gws = A.g_wsum ? __ldg(A.g_wsum + ray) : 0.f;
+    const uint64_t rg = A.ray_offset + ray;
+    __syncthreads();
+    for (int i = tid; i < L4D_ENC; i += 256) {
+      const int dim = i / 24, k = (i % 24) >> 1, ph = i & 1;
+      s_enc[i] = l4d_freq(dim == 0 ? dx : (dim == 1 ? dy : dz), k, ph);
+    }
+    if (tid < 128) s_csum[tid] = 0.f;
+    __syncthreads();
+    if (tid < 128) {
+      const float c = l4d_attr_cdir(M, tid >> 6, tid & 63, s_enc);
+      s_cdir[tid] = c;
+      s_cdir2[tid] = c - l4d_ld1(M.att_w1t[tid >> 6] + (size_t)M.attr_in_dim * L4D_H + (tid & 63));
+    }
+    __syncthreads();
+    {   // pass 1: transmittance at the start of every tile
+      float carry = 1.f;
+      for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t j = (uint32_t)t * 128 + row;
+        float v = 1.f;
+        if (j < S) {
+          const float zj = l4d_z(rs, rg, j);
+          const float delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
+          v = (1.0f - l4d_alpha(M, delta, A.sv.sigma[(size_t)ray * S + j])) + 1e-15f;
+        }
+        if (tid == 0) s_tstart[t] = carry;
+        float total;
+        half_excl_prod(v, s_w, total);
+        carry *= total;
+      }
+    }
+    __syncthreads();
+    float suffix = 0.f;
+    for (int t = n_tiles - 1; t >= 0; --t) {
+      const uint32_t j = (uint32_t)t * 128 + row;
+      const bool active = j < S;
+      const size_t p = (size_t)ray * S + (active ? j : 0);
+      bool masked = false;
+      float dsigma = 0.f, da[2] = {0.f, 0.f};
+      {
+        float v = 1.f, alpha = 0.f, gw = 0.f, delta = 0.f;
+        if (active) {
+          const float zj = l4d_z(rs, rg, j);
+          delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
+          alpha = l4d_alpha(M, delta, A.sv.sigma[p]);
+          v = (1.0f - alpha) + 1e-15f;
+          gw = gd * zj + gi0 * A.sv.attr[p] + gi1 * A.sv.attr[A.sv.P + p] + gws;
+          if (A.g_weights) gw += __ldg(A.g_weights + p);
+        }
+        float total, qtot;
+        const float T = s_tstart[t] * half_excl_prod(v, s_w, total);
+        const float w = alpha * T;
+        const float suf = suffix + half_excl_suffix_sum(gw * w, s_w, qtot);
+        suffix += qtot;
+        if (active) {
+          dsigma = (gw * T - suf / v) * (kk * delta * M.density_scale) * (1.0f - alpha);
+          masked = w > 1e-4f;
+          if (masked) { da[0] = w * gi0; da[1] = w * gi1; }
+        }
+      }
+
+      // ---------------- P1: sigma MLP forward ----------------
+      load_x(p, active);
+      ms.publish();
+      if (tid == 0) {
+        mma_chunks(tm + 0, aXh, sb + L.w1, 64, n_xchunks, false);
+        mma_chunks(tm + 0, aXl, sb + L.w1, 64, n_xchunks, true);
+        ms.commit();
+      }
+      ms.wait();
+      uint32_t msk = 0u;                       // relu pattern of this half's 32 hidden units
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+        const int q = 2 * half + qq;
+        float v[16];
+        tmem_ld16(tlane + (uint32_t)(q * 16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool on = v[i] > 0.f;
+          v[i] = on ? v[i] : 0.f;
+          msk |= on ? (1u << (qq * 16 + i)) : 0u;
+        }
+        tile_put8(hh, hl, row, 2 * q, v);
+        tile_put8(hh, hl, row, 2 * q + 1, v + 8);
+      }
+      ms.publish();
+      if (tid == 0) {
+        mma_chunks(tm + 128, aHh, sb + L.w2, 16, 8, false);
+        mma_chunks(tm + 128, aHl, sb + L.w2, 16, 8, true);
+        ms.commit();
+      }
+      ms.wait();
+      float out[16], dgeo[16];
+      tmem_ld16(tlane + 128u, out);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dgeo[i] = 0.f;
+
+      // ---------------- P2: attribute heads ----------------
+      if (__syncthreads_or(masked ? 1 : 0)) {
+        {   // [geo, 1] tile (zero rows for samples outside the attribute mask)
+          float g[16];
+#pragma unroll
+          for (int i = 0; i < 15; ++i) g[i] = masked ? out[1 + i] : 0.f;
+          g[15] = masked ? 1.0f : 0.f;
+          tile_put8(g16h, g16l, row, half, g + 8 * half);
+        }
+#pragma unroll 1
+        for (int net = 0; net < 2; ++net) {
+          if (block_amax256(da[net], s_w) == 0.f) continue;       // no gradient reaches this head in this tile
+          ms.publish();
+          if (tid == 0) {
+            mma_chunks(tm + 0, aG16h, sb + L.wa1[net], 64, 2, false);
+            mma_chunks(tm + 0, aG16l, sb + L.wa1[net], 64, 2, true);
+            ms.commit();
+          }
+          ms.wait();
+          uint32_t m1 = 0u;
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {
+            const int q = 2 * half + qq;
+            float v[16];
+            tmem_ld16(tlane + (uint32_t)(q * 16), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float y = v[i] + s_cdir2[net * 64 + q * 16 + i];
+              const bool on = y > 0.f;
+              v[i] = on ? y : 0.f;
+              m1 |= on ? (1u << (qq * 16 + i)) : 0u;
+            }
+            tile_put8(t1h, t1l, row, 2 * q, v);
+            tile_put8(t1h, t1l, row, 2 * q + 1, v + 8);
+          }
+          ms.publish();
+          if (tid == 0) {
+            mma_chunks(tm + 64, aT1h, sb + L.wa2[net], 64, 8, false);
+            mma_chunks(tm + 64, aT1l, sb + L.wa2[net], 64, 8, true);
+            ms.commit();
+          }
+          ms.wait();
+          float cs = 1.0f;
+          {   // output layer (fp32), sigmoid backward, delta of the second hidden layer
+            float o = 0.f;
+            uint32_t m2 = 0u;
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              const int q = 2 * half + qq;
+              float v[16];
+              tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool on = v[i] > 0.f;
+                v[i] = on ? v[i] : 0.f;
+                m2 |= on ? (1u << (qq * 16 + i)) : 0u;
+                o = fmaf(v[i], l4d_ld1(M.att_w3[net] + q * 16 + i), o);
+              }
+              tile_put8(t2h, t2l, row, 2 * q, v);
+              tile_put8(t2h, t2l, row, 2 * q + 1, v + 8);
+            }
+            s_part[half * 128 + row] = o;           // the two halves of the row exchange their partial dot products
+            __syncthreads();
+            o = s_part[row] + s_part[128 + row];
+            const float a = l4d_sigmoid(o);
+            const float d_raw = masked ? da[net] * a * (1.0f - a) : 0.f;
+            // per-tile power-of-two scale of the delta tiles (|w3| <= w3max bounds the second tile too)
+            const float am = block_amax256(d_raw * s_w3max[net], s_w);
+            cs = am > 0.f ? pow2_factor(am) : 1.0f;
+            const float d_o = d_raw * cs;
+            if (half == 0) {
+              float d8[8] = {d_o, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              tile_put8(o8h, o8l, row, 0, d8);
+            }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const int q = 4 * half + qq;
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = ((m2 >> (qq * 8 + i)) & 1u) ? l4d_ld1(M.att_w3[net] + q * 8 + i) * d_o : 0.f;
+              tile_put8(t3h, t3l, row, q, v);
+            }
+          }
+          ms.publish();
+          if (tid == 0) {
+            // dw3^T[64 x 8] = H2^T * dO
+            mma_tt(tm + 176, aT2h, 64, aO8h, 8, false);
+            mma_tt(tm + 176, aT2l, 64, aO8h, 8, true);
+            mma_tt(tm + 176, aT2h, 64, aO8l, 8, true);
+            // dW2^T[64 x 64] = H1^T * dH2
+            mma_tt(tm + 192, aT1h, 64, aT3h, 64, false);
+            mma_tt(tm + 192, aT1l, 64, aT3h, 64, true);
+            mma_tt(tm + 192, aT1h, 64, aT3l, 64, true);
+            // dH1[128 x 64] = dH2 * W2
+            mma_prop(tm + 0, aT3h, 8, sb + L.wa2[net], 64, 64, false);
+            mma_prop(tm + 0, aT3l, 8, sb + L.wa2[net], 64, 64, true);
+            ms.commit();
+          }
+          ms.wait();
+          const float inv = 1.0f / cs;
+          float cs2;
+          {   // re-scale the propagated delta with its own amax, then dH1 * relu1 -> T2 (H2 is dead)
+            float am = 0.f;
+            float vv[2][16];
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              tmem_ld16(tlane + (uint32_t)((2 * half + qq) * 16), vv[qq]);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                vv[qq][i] = ((m1 >> (qq * 16 + i)) & 1u) ? vv[qq][i] : 0.f;
+                am = fmaxf(am, fabsf(vv[qq][i]));
+              }
+            }
+            am = block_amax256(am, s_w);
+            const float r = am > 0.f ? pow2_factor(am) : 1.0f;
+            cs2 = cs * r;
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              const int q = 2 * half + qq;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) vv[qq][i] *= r;
+              tile_put8(t2h, t2l, row, 2 * q, vv[qq]);
+              tile_put8(t2h, t2l, row, 2 * q + 1, vv[qq] + 8);
+            }
+          }
+          const float inv2 = 1.0f / cs2;
+          {   // flush dw3 and dW2^T (rows live in lanes < 16 of every warp; columns split between the halves)
+            float v[16];
+            tmem_ld16(tlane + 176u, v);        // 8 valid columns; column 0 = dw3[row]
+            if (has64 && half == 0) atomicAdd(G.att_w3[net] + row64, v[0] * inv);
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              const int q = 2 * half + qq;
+              tmem_ld16(tlane + 192u + (uint32_t)(q * 16), v);
+              if (has64) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) atomicAdd(G.att_w2t[net] + (size_t)row64 * 64 + q * 16 + i, v[i] * inv);
+              }
+            }
+          }
+          ms.publish();
+          if (tid == 0) {
+            // dW1g[64 x 16] = dH1^T * [geo,1]
+            mma_tt(tm + 160, aT2h, 64, aG16h, 16, false);
+            mma_tt(tm + 160, aT2l, 64, aG16h, 16, true);
+            mma_tt(tm + 160, aT2h, 64, aG16l, 16, true);
+            // dG[128 x 16] = dH1 * W1g
+            mma_prop(tm + 128, aT2h, 8, sb + L.wa1[net], 64, 16, false);
+            mma_prop(tm + 128, aT2l, 8, sb + L.wa1[net], 64, 16, true);
+            ms.commit();
+          }
+          ms.wait();
+          {
+            float v[16];
+            tmem_ld16(tlane + 128u, v);
+#pragma unroll
+            for (int i = 0; i < 15; ++i) dgeo[i] = fmaf(v[i], inv2, dgeo[i]);
+            tmem_ld16(tlane + 160u, v);
+            if (has64) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int ii = 8 * half + i;
+                if (ii < 15) atomicAdd(G.att_w1t[net] + (size_t)(L4D_ENC + ii) * 64 + row64, v[ii] * inv2);
+              }
+              if (half == 1) s_csum[net * 64 + row64] += v[15] * inv2;
+            }
+          }
+          tc_fence_before();
+          __syncthreads();
+          tc_fence_after();
+        }
+      }
+
+      // ---------------- P3: sigma MLP backward ----------------
+      float d16[16];
+      d16[0] = active ? dsigma * expf(fminf(fmaxf(out[0], -15.f), 15.f)) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 15; ++i) d16[1 + i] = active ? dgeo[i] : 0.f;
+      float am = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) am = fmaxf(am, fabsf(d16[i]));
+      const float amax = block_amax256(am, s_w);
+      if (amax == 0.f) {           // nothing flows back through this tile
+        if (active) for (int k = 0; k < (int)M.sigma_in_dim; ++k) A.sv.dfeat[(size_t)k * A.sv.P + p] = 0.f;
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        continue;
+      }
+      const float sc = pow2_factor(amax);
+      float inv = 1.0f / sc;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) d16[i] *= sc;
+      tile_put8(o16h, o16l, row, half, d16 + 8 * half);
+      ms.publish();
+      if (tid == 0) {
+        // dHs[128 x 64] = dO * W2   (W2 stored [k/8][16 rows][8])
+        mma_prop(tm + 64, aO16h, 2, sb + L.w2, 16, 64, false);
+        mma_prop(tm + 64, aO16l, 2, sb + L.w2, 16, 64, true);
+        // dW2s^T[64 x 16] = Hs^T * dO
+        mma_tt(tm + 144, aHh, 64, aO16h, 16, false);
+        mma_tt(tm + 144, aHl, 64, aO16h, 16, true);
+        mma_tt(tm + 144, aHh, 64, aO16l, 16, true);
+        ms.commit();
+      }
+      ms.wait();
+      {
+        float v[16];
+        tmem_ld16(tlane + 144u, v);
+        if (has64) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) atomicAdd(G.sig_w2 + (size_t)(8 * half + o) * 64 + row64, v[8 * half + o] * inv);
+        }
+      }
+      {   // re-scale the propagated delta with its own amax, then dHs * relu -> RH (hidden is dead)
+        float am2 = 0.f;
+        float vv[2][16];
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          tmem_ld16(tlane + 64u + (uint32_t)((2 * half + qq) * 16), vv[qq]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            vv[qq][i] = ((msk >> (qq * 16 + i)) & 1u) ? vv[qq][i] : 0.f;
+            am2 = fmaxf(am2, fabsf(vv[qq][i]));
+          }
+        }
+        am2 = block_amax256(am2, s_w);
+        const float r = am2 > 0.f ? pow2_factor(am2) : 1.0f;
+        inv = 1.0f / (sc * r);
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int q = 2 * half + qq;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) vv[qq][i] *= r;
+          tile_put8(hh, hl, row, 2 * q, vv[qq]);
+          tile_put8(hh, hl, row, 2 * q + 1, vv[qq] + 8);
+        }
+      }
+      // ---------------- P4: input gradients and first-layer weight gradient ----------------
+      load_x(p, active);
+      ms.publish();
+      if (tid == 0) {
+        // dX[128 x in_pad] = dHs * W1   (W1 stored [k/8][64 rows][8])
+        mma_prop(tm + 256, aHh, 8, sb + L.w1, 64, in_pad, false);
+        mma_prop(tm + 256, aHl, 8, sb + L.w1, 64, in_pad, true);
+        // dW1^T[in x 64] = X^T * dHs : rows 0..127, then rows 128..191
+        mma_tt(tm + 192, aXh, 128, aHh, 64, false);
+        mma_tt(tm + 192, aXl, 128, aHh, 64, true);
+        mma_tt(tm + 192, aXh, 128, aHl, 64, true);
+        if (in_pad > 128) {
+          mma_tt(tm + 448, aXh + 16u * 2048u, 64, aHh, 64, false);
+          mma_tt(tm + 448, aXl + 16u * 2048u, 64, aHh, 64, true);
+          mma_tt(tm + 448, aXh + 16u * 2048u, 64, aHl, 64, true);
+        }
+        ms.commit();
+      }
+      ms.wait();
+      for (int q = half; q < (int)in_pad / 16; q += 2) {
+        float v[16];
+        tmem_ld16(tlane + 256u + (uint32_t)(q * 16), v);
+        if (active) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = q * 16 + i;
+            if (k < (int)M.sigma_in_dim) A.sv.dfeat[(size_t)k * A.sv.P + p] = v[i] * inv;
+          }
+        }
+      }
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+        const int q = 2 * half + qq;
+        float v[16];
+        tmem_ld16(tlane + 192u + (uint32_t)(q * 16), v);
+        if (row < (int)in_pad) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(G.sig_w1t + (size_t)row * 64 + q * 16 + i, v[i] * inv);
+        }
+      }
+      if (in_pad > 128) {
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int q = 2 * half + qq;
+          float v[16];
+          tmem_ld16(tlane + 448u + (uint32_t)(q * 16), v);
+          if (has64 && 128 + row64 < (int)in_pad) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(G.sig_w1t + (size_t)(128 + row64) * 64 + q * 16 + i, v[i] * inv);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+    // direction / ones rows of the first attribute layer: dW1t[k][j] += enc[k] * sum_samples dh1[j]
+    __syncthreads();
+    for (int i = tid; i < 2 * (L4D_ENC + 9) * 64; i += 256) {
+      const int net = i / ((L4D_ENC + 9) * 64);
+      const int r = (i / 64) % (L4D_ENC + 9), jx = i & 63;
+      const float cs = s_csum[net * 64 + jx];
+      if (r < L4D_ENC) atomicAdd(G.att_w1t[net] + (size_t)r * 64 + jx, s_enc[r] * cs);
+      else atomicAdd(G.att_w1t[net] + (size_t)(M.attr_in_dim + (r - L4D_ENC)) * 64 + jx, cs);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
 // =============================================================================================
 // flow MLP (16 -> 64 -> 64 -> 6) on tensor cores
 // =============================================================================================

@@ -948,9 +948,10 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
     if (cfg->mlp_fp16 && cfg->sigma_in_pad <= 192) {
       const size_t smem = dense_bwd_smem(cfg->sigma_in_pad).total + 1024;
       int grid;
-      rc = grid_for(k_bwd_dense_tc, 128, smem, rays->n_rays, grid);
+      // 256-thread variant (two threads per row); the 128-thread kernel stays as the readable reference version
+      rc = grid_for(k_bwd_dense_tc2, 256, smem, rays->n_rays, grid);
       if (rc != L4D_OK) return rc;
-      k_bwd_dense_tc<<<grid, 128, smem, st>>>(A);
+      k_bwd_dense_tc2<<<grid, 256, smem, st>>>(A);
       prof_mark(st, "k_bwd_dense_tc");
     } else {
       const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD + 80 + 128 + 128 + 32 + L4D_MAX_TILES) * sizeof(float);
