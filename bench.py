@@ -84,7 +84,8 @@ def kernel_bytes(cfg):
         "k_fwd_flow": 8 * 8 * 16 + 4 * 22,                                 # flow-grid gather + flow-in / flow planes written
         "k_fwd_dense": 4 * D + 12,                                          # features read, sigma/attr saved
         "k_bwd_dense": 2 * 4 * D + 4 * D + 12,                              # features read twice, dfeat written
-        "k_bwd_scatter": 2 * (L * 8 * 16 + 3 * 2 * L * 4 * 16 + 4 * planes) + 4 * planes + 4 * D + 48,
+        "k_bwd_scatter": 2 * (3 * 2 * L * 4 * 16 + 4 * planes) + 4 * planes + 4 * (D - 4 * L) + 48,
+        "k_bwd_scatter_static": 2 * (L * 8 * 16) + 4 * 4 * L,
         "k_bwd_flow": 4 * 22 + 4 * 16,                                       # dflow + flow-in read, dfin written
         "k_bwd_flowgrid": 2 * (8 * 8 * 32) + 4 * 16,
     }

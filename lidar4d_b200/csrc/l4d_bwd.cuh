@@ -265,7 +265,7 @@ struct DfeatFromPlane {
 };
 
 // scatter dL/dfeature through the encoders of one sample at (x,y,z) with its flow; dflow[6] out
-template <bool WARP_AGG, class DF>
+template <bool WARP_AGG, class DF, bool STATIC_HASH = true>
 L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
                              const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6], bool active);
 
@@ -279,7 +279,7 @@ L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads&
 
 // WARP_AGG: every lane of the warp must call (lanes without a sample pass active=false and a
 // provider that returns 0; they take part in the plane aggregation with zero contributions)
-template <bool WARP_AGG, class DF>
+template <bool WARP_AGG, class DF, bool STATIC_HASH>
 L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
                              const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6], bool active) {
 #pragma unroll
@@ -350,9 +350,10 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
   }
 
   if (!active) return;
-  // static hash: dL/dtable[entry] += w_corner * dfeat[0..4)
+  // static hash: dL/dtable[entry] += w_corner * dfeat[0..4)   (the split pipeline does this level-major in
+  // k_bwd_scatter_static so that only one level's 8 MB of gradients is live in L2 at a time)
 #pragma unroll 1
-  for (int l = 0; l < L; ++l) {
+  for (int l = 0; STATIC_HASH && l < L; ++l) {
     uint32_t idx[8]; float w[8];
     l4d_corners3(M.gs, l, x, y, z, idx, w);
     const float d0 = l4d_dfeat_fn(row_hash_s + 4 * l + 0), d1 = l4d_dfeat_fn(row_hash_s + 4 * l + 1);

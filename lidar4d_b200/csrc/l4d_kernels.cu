@@ -968,6 +968,10 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
       if (rc != L4D_OK) return rc;
       k_bwd_scatter<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
       prof_mark(st, "k_bwd_scatter");
+      rc = grid_for(k_bwd_scatter_static<L4D_NT>, L4D_NT, 0, tiles, grid);
+      if (rc != L4D_OK) return rc;
+      k_bwd_scatter_static<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
+      prof_mark(st, "k_bwd_scatter_static");
     }
     if (frame->has_fwd || frame->has_bwd) {     // with no neighbour frame nothing reaches the flow field
       if (cfg->mlp_fp16) {

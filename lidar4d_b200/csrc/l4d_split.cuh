@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(NT, L4D_SCATTER_MIN_CTAS) k_bwd_scatter(const 
 #pragma unroll
     for (int k = 0; k < 6; ++k) flow[k] = A.sv.flow[(size_t)k * P + p];
     DfeatFromPlaneMasked df{A.sv.dfeat + p, P, active};
-    l4d_bw_scatter_t<true>(M, A.F, A.G, x, y, z, flow, df, dflow, active);
+    l4d_bw_scatter_t<true, DfeatFromPlaneMasked, false>(M, A.F, A.G, x, y, z, flow, df, dflow, active);
     if (active) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) A.sv.dflow[(size_t)k * P + p] = dflow[k];
@@ -405,6 +405,38 @@ __global__ void __launch_bounds__(NT, 4) k_bwd_flowgrid(const __grid_constant__ 
           l4d_red4(q + 4, w[c] * b[2] * d0, w[c] * b[2] * d1, w[c] * b[3] * d0, w[c] * b[3] * d1);
         }
       }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// backward 2b: static-hash reductions, LEVEL-MAJOR.  The fp32 gradient of the static table is 8 MB per level
+// (134 MB at L=16, more than the 126 MB L2): walking all levels per sample made the reductions miss in L2
+// (ncu: 31 GB of DRAM traffic, L2 hit 59 %).  Here every CTA sweeps the samples once per level, so the whole
+// chip works on one level at a time and its gradient slab stays L2-resident.
+// -------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 8) k_bwd_scatter_static(const __grid_constant__ SplitArgs A) {
+  const DevModel& M = A.M;
+  const size_t P = A.sv.P;
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  const int L = (int)M.gs.n_levels;
+  const int row_hash_s = 2 * (int)M.n_scales * 8;
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    float* gbase = A.G.hs + (size_t)M.gs.offset[l] * 4;
+    const float* d = A.sv.dfeat + (size_t)(row_hash_s + 4 * l) * P;
+    for (size_t p = (size_t)blockIdx.x * NT + threadIdx.x; p < P; p += (size_t)gridDim.x * NT) {
+      const float d0 = __ldg(d + p), d1 = __ldg(d + P + p), d2 = __ldg(d + 2 * P + p), d3 = __ldg(d + 3 * P + p);
+      const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
+      const float zj = l4d_z(rs, A.ray_offset + ray, j);
+      const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
+      const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
+      const float z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
+      uint32_t idx[8]; float w[8];
+      l4d_corners3(M.gs, l, x, y, z, idx, w);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) l4d_red4(gbase + (size_t)idx[c] * 4, w[c] * d0, w[c] * d1, w[c] * d2, w[c] * d3);
     }
   }
 }
