@@ -91,16 +91,31 @@ struct DevGrads {
 // where the training-mode forward saves what the backward needs: SoA planes of
 // P = n_rays*n_steps floats each -> every warp store / load is one 128 B line
 struct SavedView {
-  float* feat;      // [sigma_in_dim][P]
+  float* feat;      // [sigma_in_dim][P]   (fp32-FMA dense kernels)
+  unsigned char* feat_tc;   // same region in the tensor-core path: per 128-sample tile of a ray, the fp16 operand tile
+                            // itself: [ray][tile][hi|lo][k/8][128 rows][8 halves]  -> one bulk copy into shared memory
   float* flow_in;   // [16][P]
   float* sigma;     // [P]
   float* attr;      // [2][P]
   float* hidden;    // [ctas][64][NT] per-CTA scratch of the dense backward kernel
   float* flow;      // [6][P]   flow-field output (split pipeline: the scatter kernel needs the warped positions)
-  float* dfeat;     // [sigma_in_dim][P]  dL/dfeature, dense backward -> scatter kernel
+  float* dfeat;     // dL/dfeature, dense backward -> scatter kernels: [ray][tile][k/4][128 rows][4] (float4 per row)
   float* dflow;     // [6][P]   dL/dflow, scatter kernel -> flow backward kernel
   size_t P;
+  uint32_t n_tiles;   // 128-sample tiles per ray
+  uint32_t x_chunks;  // stored 16-byte chunks per row of a feature tile = ceil(sigma_in_dim / 8)
+  uint32_t d_quads;   // float4 per row of a dfeat tile = ceil(sigma_in_dim / 4)
 };
+
+// float offset of (sample j of ray, feature 0) in the dfeat tiles; feature k lives at + (k >> 2) * 512 + (k & 3)
+L4D_HD size_t l4d_dfeat_off(const SavedView& sv, uint32_t ray, uint32_t j) {
+  return (((size_t)ray * sv.n_tiles + (j >> 7)) * sv.d_quads * 128 + (j & 127)) * 4;
+}
+L4D_HD size_t l4d_dfeat_k(int k) { return (size_t)(k >> 2) * 512 + (size_t)(k & 3); }
+// byte offset of the hi half of the feature tile holding sample j of ray, at the sample's row (chunk 0)
+L4D_HD size_t l4d_feat_tc_off(const SavedView& sv, uint32_t ray, uint32_t j) {
+  return ((size_t)ray * sv.n_tiles + (j >> 7)) * ((size_t)sv.x_chunks * 4096) + (size_t)(j & 127) * 16;
+}
 
 // ---------------------------------------------------------------------------
 // small load / reduce wrappers (device: read-only path + vector RED; host: plain)
@@ -550,7 +565,51 @@ struct FeatSink {
   size_t P;         // plane stride
   size_t p;         // this sample
   float* dense;     // optional dense [sigma_in_dim] row (debug entry point) or nullptr
+  unsigned char* tile = nullptr;   // tensor-core path: this sample's row in the hi half of its fp16 feature tile
+  uint32_t tile_lo = 0;            // byte distance from the hi half to the lo half
 };
+
+#if defined(__CUDA_ARCH__)
+// features [row0, row0+n) of one sample as fp16 hi + lo (x = hi + lo to ~2^-22) into its operand tile.
+// 8-aligned groups are one 16-byte store per half (a warp writes 512 contiguous bytes), 4-aligned groups 8 bytes.
+__device__ __forceinline__ void l4d_tile_emit(unsigned char* hi, uint32_t lo_off, int row0, int n, const float* xb, int xs) {
+  int i = 0;
+  while (i < n) {
+    const int k = row0 + i;
+    unsigned char* q = hi + (size_t)(k >> 3) * 2048 + (size_t)(k & 7) * 2;
+    if ((k & 3) == 0 && i + 4 <= n) {
+      const bool full = (k & 7) == 0 && i + 8 <= n;
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u < 2 || full) {
+          const float a = xb[(i + 2 * u) * xs], b = xb[(i + 2 * u + 1) * xs];
+          const __half2 hh = __floats2half2_rn(a, b);
+          const float2 f = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(a - f.x, b - f.y);
+          h[u] = *reinterpret_cast<const uint32_t*>(&hh);
+          l[u] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+      }
+      if (full) {
+        *reinterpret_cast<uint4*>(q) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(q + lo_off) = make_uint4(l[0], l[1], l[2], l[3]);
+        i += 8;
+      } else {
+        *reinterpret_cast<uint2*>(q) = make_uint2(h[0], h[1]);
+        *reinterpret_cast<uint2*>(q + lo_off) = make_uint2(l[0], l[1]);
+        i += 4;
+      }
+    } else {
+      const float a = xb[i * xs];
+      const __half hh = __float2half_rn(a);
+      *reinterpret_cast<__half*>(q) = hh;
+      *reinterpret_cast<__half*>(q + lo_off) = __float2half_rn(a - __half2float(hh));
+      i += 1;
+    }
+  }
+}
+#endif
 
 // push n feature values (held in the exchange column xb[0..n)) to the sinks and, when ACC, into the
 // first sigma layer.  The split pipeline (k_fwd_gather) runs with ACC=false: no MLP registers live
@@ -561,6 +620,9 @@ L4D_HD void l4d_emit(float (&acc)[L4D_H], const DevModel& M, float* xb, int xs, 
   if (sink.feat) {
     for (int i = 0; i < n; ++i) sink.feat[(size_t)(row0 + i) * sink.P + sink.p] = xb[i * xs];
   }
+#if defined(__CUDA_ARCH__)
+  if (sink.tile) l4d_tile_emit(sink.tile, sink.tile_lo, row0, n, xb, xs);
+#endif
   if (sink.dense) {
     for (int i = 0; i < n; ++i) sink.dense[row0 + i] = xb[i * xs];
   }

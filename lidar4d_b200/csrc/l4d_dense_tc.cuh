@@ -102,7 +102,7 @@ __host__ __device__ inline DenseFwdSmem dense_fwd_smem(uint32_t in_pad) {
 __global__ void __launch_bounds__(128) k_fwd_dense_tc(const __grid_constant__ SplitArgs A) {
   using namespace l4dtc;
   extern __shared__ __align__(1024) unsigned char dsm[];
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar, s_xbar;
   __shared__ uint32_t s_tmem;
   const DevModel& M = A.M;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) k_fwd_dense_tc(const __grid_constant__ Sp
   float* s_w = s_cdir + 128;
   const uint32_t sb = smem_u32(dsm);
 
-  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&s_bar, 1); mbar_init(&s_xbar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&s_tmem, 512);
   // weights -> shared memory (already in operand layout in global memory)
   {
@@ -135,6 +135,29 @@ __global__ void __launch_bounds__(128) k_fwd_dense_tc(const __grid_constant__ Sp
   const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
   const uint32_t S = A.S;
   const int n_xchunks = (int)in_pad / 8;
+  // feature tiles arrive as fp16 hi|lo operand tiles (written by k_fwd_gather) with one bulk copy per half; the copy of
+  // the next tile is issued as soon as the last MMA that reads the X buffer has completed
+  const uint32_t xbytes = A.sv.x_chunks * 2048u;
+  const uint32_t n_tiles = A.sv.n_tiles;
+  uint32_t xphase = 0u;
+  auto x_issue = [&](uint32_t r, uint32_t t) {
+    // tcnn's ones-padding chunks are not stored in global memory
+    for (int c = (int)A.sv.x_chunks; c < n_xchunks; ++c) {
+      *reinterpret_cast<uint4*>(tile_chunk(xh, tid, c)) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+      *reinterpret_cast<uint4*>(tile_chunk(xl, tid, c)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+      const unsigned char* src = A.sv.feat_tc + ((size_t)r * n_tiles + t) * (size_t)(2u * xbytes);
+      mbar_expect_tx(&s_xbar, 2u * xbytes);
+      bulk_g2s(sb + L.xh, src, xbytes, &s_xbar);
+      bulk_g2s(sb + L.xl, src + xbytes, xbytes, &s_xbar);
+    }
+  };
+  auto x_issue_next = [&](uint32_t r, uint32_t t) {
+    if (t + 1 < n_tiles) x_issue(r, t + 1);
+    else if (r + gridDim.x < A.n_rays) x_issue(r + gridDim.x, 0u);
+  };
+  if (blockIdx.x < A.n_rays) x_issue(blockIdx.x, 0u);
 
   for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
     const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
@@ -152,22 +175,8 @@ __global__ void __launch_bounds__(128) k_fwd_dense_tc(const __grid_constant__ Sp
       const uint32_t j = j0 + tid;
       const bool valid = j < S;
       const size_t p = (size_t)ray * S + (valid ? j : 0);
-      // ---- features -> hi/lo tile (coalesced SoA reads, one 16-byte chunk per 8 features) ----
-      // 4 chunks (32 independent coalesced loads) in flight per thread: with 4 warps per SM the HBM round trip
-      // has to be covered by memory-level parallelism inside the thread
-      for (int c0 = 0; c0 < n_xchunks; c0 += 4) {
-        float v[4][8];
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int k = (c0 + cc) * 8 + i;
-            v[cc][i] = (!valid || k >= (int)in_pad) ? 0.f : (k < (int)M.sigma_in_dim ? __ldg(A.sv.feat + (size_t)k * A.sv.P + p) : 1.0f);
-          }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          if (c0 + cc < n_xchunks) tile_put8(xh, xl, tid, c0 + cc, v[cc]);
-      }
+      mbar_wait(&s_xbar, xphase);      // this tile's features have landed
+      xphase ^= 1u;
       ms.publish();
       if (tid == 0) {
         mma_chunks(tm + 0, sb + L.xh, sb + L.w1, 64, n_xchunks, false);
@@ -208,7 +217,9 @@ __global__ void __launch_bounds__(128) k_fwd_dense_tc(const __grid_constant__ Sp
       const float w = alpha * T;
       const bool masked = valid && w > 1e-4f;
       float a0 = 0.f, a1 = 0.f;
-      if (__syncthreads_or(masked ? 1 : 0)) {
+      const bool any_masked = __syncthreads_or(masked ? 1 : 0) != 0;
+      if (!any_masked) x_issue_next(ray, j0 >> 7);       // the X buffer is free already
+      if (any_masked) {
         // ---- attribute heads: [geo,0] (K=16) -> 2x64 -> relu -> 64 -> relu -> dot w3 -> sigmoid ----
         float g[16];
 #pragma unroll
@@ -242,6 +253,7 @@ __global__ void __launch_bounds__(128) k_fwd_dense_tc(const __grid_constant__ Sp
           ms.commit();
         }
         ms.wait();
+        x_issue_next(ray, j0 >> 7);                    // the attribute hidden tile (in the X buffer) has been consumed
         float o[2] = {0.f, 0.f};
 #pragma unroll
         for (int net = 0; net < 2; ++net) {
@@ -351,485 +363,6 @@ __device__ __forceinline__ float pow2_factor(float amax) {
 }
 }  // namespace l4dtc
 
-__global__ void __launch_bounds__(128) k_bwd_dense_tc(const __grid_constant__ SplitArgs A) {
-  using namespace l4dtc;
-  extern __shared__ __align__(1024) unsigned char dsm[];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint32_t s_tmem;
-  const DevModel& M = A.M;
-  const DevGrads& G = A.G;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t in_pad = M.sigma_in_pad;
-  const DenseBwdSmem L = dense_bwd_smem(in_pad);
-  const uint32_t sb = smem_u32(dsm);
-  // tile views
-  unsigned char* xh = dsm + L.R;                 // X hi: 24 chunks
-  unsigned char* xl = dsm + L.R + 48 * 1024;     // X lo
-  unsigned char* t1h = dsm + L.R, *t1l = t1h + 16384;              // T1
-  unsigned char* t2h = dsm + L.R + 32768, *t2l = t2h + 16384;      // T2
-  unsigned char* t3h = dsm + L.R + 65536, *t3l = t3h + 16384;      // T3
-  unsigned char* hh = dsm + L.RH, *hl = hh + 16384;
-  unsigned char* g16h = dsm + L.g16, *g16l = g16h + 4096;
-  unsigned char* o16h = dsm + L.do16, *o16l = o16h + 4096;
-  unsigned char* o8h = dsm + L.do8, *o8l = o8h + 2048;
-  const uint32_t aXh = sb + L.R, aXl = aXh + 48 * 1024;
-  const uint32_t aT1h = sb + L.R, aT1l = aT1h + 16384, aT2h = aT1h + 32768, aT2l = aT2h + 16384, aT3h = aT1h + 65536, aT3l = aT3h + 16384;
-  const uint32_t aHh = sb + L.RH, aHl = aHh + 16384;
-  const uint32_t aG16h = sb + L.g16, aG16l = aG16h + 4096, aO16h = sb + L.do16, aO16l = aO16h + 4096, aO8h = sb + L.do8, aO8l = aO8h + 2048;
-  float* s_enc = reinterpret_cast<float*>(dsm + L.misc);
-  float* s_cdir = s_enc + 80;      // full per-ray first-layer term (as the forward uses it)
-  float* s_cdir2 = s_cdir + 128;   // same minus the first ones-row (the tile's column 15 carries that 1)
-  float* s_csum = s_cdir2 + 128;
-  float* s_w = s_csum + 128;
-  float* s_tstart = s_w + 32;
-  __shared__ float s_w3max[2];
-
-  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(&s_tmem, 512);
-  if (tid < 2) {
-    float m = 1.0f;
-    for (int k = 0; k < 64; ++k) m = fmaxf(m, fabsf(l4d_ld1(M.att_w3[tid] + k)));
-    s_w3max[tid] = m;
-  }
-  {
-    auto cp = [&](uint32_t off, const __half* src, uint32_t bytes) {
-      for (uint32_t i = tid * 16; i < bytes; i += 128 * 16)
-        *reinterpret_cast<uint4*>(dsm + off + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(src) + i));
-    };
-    cp(L.w1, M.tc_sig_w1, in_pad * 64 * 2);
-    cp(L.w2, M.tc_sig_w2, 64 * 16 * 2);
-    cp(L.wa1[0], M.tc_att_w1g_net[0], 16 * 64 * 2);
-    cp(L.wa1[1], M.tc_att_w1g_net[1], 16 * 64 * 2);
-    cp(L.wa2[0], M.tc_att_w2[0], 64 * 64 * 2);
-    cp(L.wa2[1], M.tc_att_w2[1], 64 * 64 * 2);
-  }
-  MmaSync ms{&s_bar, 0u};
-  ms.publish();
-  const uint32_t tm = s_tmem;
-  const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16);
-  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
-  const uint32_t S = A.S;
-  const int n_tiles = (int)((S + 127) / 128);
-  const float kk = M.active_sensor ? 2.0f : 1.0f;
-  const int n_xchunks = (int)in_pad / 8;
-  const int row64 = warp * 16 + lane;          // row held by this thread in an M=64 accumulator (lanes < 16)
-  const bool has64 = lane < 16;
-
-  // features of this thread's sample -> X tile (24 chunks, zero beyond in_pad)
-  auto load_x = [&](size_t p, bool valid) {
-    for (int c0 = 0; c0 < 24; c0 += 4) {      // 32 independent loads in flight per thread (see k_fwd_dense_tc)
-      float v[4][8];
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = (c0 + cc) * 8 + i;
-          v[cc][i] = (!valid || k >= (int)in_pad) ? 0.f : (k < (int)M.sigma_in_dim ? __ldg(A.sv.feat + (size_t)k * A.sv.P + p) : 1.0f);
-        }
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) tile_put8(xh, xl, tid, c0 + cc, v[cc]);
-    }
-  };
-
-  for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
-    const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
-    const float gd = __ldg(A.g_depth + ray), gi0 = __ldg(A.g_image + 2 * ray), gi1 = __ldg(A.g_image + 2 * ray + 1);
-    const float gws = A.g_wsum ? __ldg(A.g_wsum + ray) : 0.f;
-    const uint64_t rg = A.ray_offset + ray;
-    __syncthreads();
-    for (int i = tid; i < L4D_ENC; i += 128) {
-      const int dim = i / 24, k = (i % 24) >> 1, ph = i & 1;
-      s_enc[i] = l4d_freq(dim == 0 ? dx : (dim == 1 ? dy : dz), k, ph);
-    }
-    s_csum[tid] = 0.f;
-    __syncthreads();
-    {
-      const float c = l4d_attr_cdir(M, tid >> 6, tid & 63, s_enc);
-      s_cdir[tid] = c;
-      s_cdir2[tid] = c - l4d_ld1(M.att_w1t[tid >> 6] + (size_t)M.attr_in_dim * L4D_H + (tid & 63));
-    }
-    __syncthreads();
-    {   // pass 1: transmittance at the start of every tile
-      float carry = 1.f;
-      for (int t = 0; t < n_tiles; ++t) {
-        const uint32_t j = (uint32_t)t * 128 + tid;
-        float v = 1.f;
-        if (j < S) {
-          const float zj = l4d_z(rs, rg, j);
-          const float delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
-          v = (1.0f - l4d_alpha(M, delta, A.sv.sigma[(size_t)ray * S + j])) + 1e-15f;
-        }
-        if (tid == 0) s_tstart[t] = carry;
-        float total;
-        block_excl_prod<128>(v, s_w, total);
-        carry *= total;
-      }
-    }
-    __syncthreads();
-    float suffix = 0.f;
-    for (int t = n_tiles - 1; t >= 0; --t) {
-      const uint32_t j = (uint32_t)t * 128 + tid;
-      const bool active = j < S;
-      const size_t p = (size_t)ray * S + (active ? j : 0);
-      bool masked = false;
-      float dsigma = 0.f, da[2] = {0.f, 0.f};
-      {
-        float v = 1.f, alpha = 0.f, gw = 0.f, delta = 0.f;
-        if (active) {
-          const float zj = l4d_z(rs, rg, j);
-          delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
-          alpha = l4d_alpha(M, delta, A.sv.sigma[p]);
-          v = (1.0f - alpha) + 1e-15f;
-          gw = gd * zj + gi0 * A.sv.attr[p] + gi1 * A.sv.attr[A.sv.P + p] + gws;
-          if (A.g_weights) gw += __ldg(A.g_weights + p);
-        }
-        float total, qtot;
-        const float T = s_tstart[t] * block_excl_prod<128>(v, s_w, total);
-        const float w = alpha * T;
-        const float suf = suffix + block_excl_suffix_sum<128>(gw * w, s_w, qtot);
-        suffix += qtot;
-        if (active) {
-          dsigma = (gw * T - suf / v) * (kk * delta * M.density_scale) * (1.0f - alpha);
-          masked = w > 1e-4f;
-          if (masked) { da[0] = w * gi0; da[1] = w * gi1; }
-        }
-      }
-
-      // ---------------- P1: sigma MLP forward ----------------
-      load_x(p, active);
-      ms.publish();
-      if (tid == 0) {
-        mma_chunks(tm + 0, aXh, sb + L.w1, 64, n_xchunks, false);
-        mma_chunks(tm + 0, aXl, sb + L.w1, 64, n_xchunks, true);
-        ms.commit();
-      }
-      ms.wait();
-      uint32_t msa = 0u, msb = 0u;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[16];
-        tmem_ld16(tlane + (uint32_t)(q * 16), v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const bool on = v[i] > 0.f;
-          v[i] = on ? v[i] : 0.f;
-          const int k = q * 16 + i;
-          if (k < 32) msa |= on ? (1u << k) : 0u; else msb |= on ? (1u << (k - 32)) : 0u;
-        }
-        tile_put8(hh, hl, tid, 2 * q, v);
-        tile_put8(hh, hl, tid, 2 * q + 1, v + 8);
-      }
-      ms.publish();
-      if (tid == 0) {
-        mma_chunks(tm + 128, aHh, sb + L.w2, 16, 8, false);
-        mma_chunks(tm + 128, aHl, sb + L.w2, 16, 8, true);
-        ms.commit();
-      }
-      ms.wait();
-      float out[16], dgeo[16];
-      tmem_ld16(tlane + 128u, out);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) dgeo[i] = 0.f;
-
-      // ---------------- P2: attribute heads ----------------
-      if (__syncthreads_or(masked ? 1 : 0)) {
-        {   // [geo, 1] tile (zero rows for samples outside the attribute mask)
-          float g[16];
-#pragma unroll
-          for (int i = 0; i < 15; ++i) g[i] = masked ? out[1 + i] : 0.f;
-          g[15] = masked ? 1.0f : 0.f;
-          tile_put8(g16h, g16l, tid, 0, g);
-          tile_put8(g16h, g16l, tid, 1, g + 8);
-        }
-#pragma unroll 1
-        for (int net = 0; net < 2; ++net) {
-          if (block_amax128(da[net], s_w) == 0.f) continue;       // no gradient reaches this head in this tile
-          ms.publish();
-          if (tid == 0) {
-            mma_chunks(tm + 0, aG16h, sb + L.wa1[net], 64, 2, false);
-            mma_chunks(tm + 0, aG16l, sb + L.wa1[net], 64, 2, true);
-            ms.commit();
-          }
-          ms.wait();
-          uint32_t m1a = 0u, m1b = 0u;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[16];
-            tmem_ld16(tlane + (uint32_t)(q * 16), v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int k = q * 16 + i;
-              const float y = v[i] + s_cdir2[net * 64 + k];
-              const bool on = y > 0.f;
-              v[i] = on ? y : 0.f;
-              if (k < 32) m1a |= on ? (1u << k) : 0u; else m1b |= on ? (1u << (k - 32)) : 0u;
-            }
-            tile_put8(t1h, t1l, tid, 2 * q, v);
-            tile_put8(t1h, t1l, tid, 2 * q + 1, v + 8);
-          }
-          ms.publish();
-          if (tid == 0) {
-            mma_chunks(tm + 64, aT1h, sb + L.wa2[net], 64, 8, false);
-            mma_chunks(tm + 64, aT1l, sb + L.wa2[net], 64, 8, true);
-            ms.commit();
-          }
-          ms.wait();
-          float cs = 1.0f;
-          {   // output layer (fp32), sigmoid backward, delta of the second hidden layer
-            float o = 0.f;
-            uint32_t m2a = 0u, m2b = 0u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float v[16];
-              tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int k = q * 16 + i;
-                const bool on = v[i] > 0.f;
-                v[i] = on ? v[i] : 0.f;
-                if (k < 32) m2a |= on ? (1u << k) : 0u; else m2b |= on ? (1u << (k - 32)) : 0u;
-                o = fmaf(v[i], l4d_ld1(M.att_w3[net] + k), o);
-              }
-              tile_put8(t2h, t2l, tid, 2 * q, v);
-              tile_put8(t2h, t2l, tid, 2 * q + 1, v + 8);
-            }
-            const float a = l4d_sigmoid(o);
-            const float d_raw = masked ? da[net] * a * (1.0f - a) : 0.f;
-            // per-tile power-of-two scale of the delta tiles (|w3| <= w3max bounds the second tile too)
-            const float am = block_amax128(d_raw * s_w3max[net], s_w);
-            cs = am > 0.f ? pow2_factor(am) : 1.0f;
-            const float d_o = d_raw * cs;
-            float d8[8] = {d_o, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            tile_put8(o8h, o8l, tid, 0, d8);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int k = q * 8 + i;
-                v[i] = l4d_bit(m2a, m2b, k) ? l4d_ld1(M.att_w3[net] + k) * d_o : 0.f;
-              }
-              tile_put8(t3h, t3l, tid, q, v);
-            }
-          }
-          ms.publish();
-          if (tid == 0) {
-            // dw3^T[64 x 8] = H2^T * dO
-            mma_tt(tm + 176, aT2h, 64, aO8h, 8, false);
-            mma_tt(tm + 176, aT2l, 64, aO8h, 8, true);
-            mma_tt(tm + 176, aT2h, 64, aO8l, 8, true);
-            // dW2^T[64 x 64] = H1^T * dH2
-            mma_tt(tm + 192, aT1h, 64, aT3h, 64, false);
-            mma_tt(tm + 192, aT1l, 64, aT3h, 64, true);
-            mma_tt(tm + 192, aT1h, 64, aT3l, 64, true);
-            // dH1[128 x 64] = dH2 * W2
-            mma_prop(tm + 0, aT3h, 8, sb + L.wa2[net], 64, 64, false);
-            mma_prop(tm + 0, aT3l, 8, sb + L.wa2[net], 64, 64, true);
-            ms.commit();
-          }
-          ms.wait();
-          const float inv = 1.0f / cs;
-          float cs2;
-          {   // re-scale the propagated delta with its own amax, then dH1 * relu1 -> T2 (H2 is dead)
-            float am = 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float v[16];
-              tmem_ld16(tlane + (uint32_t)(q * 16), v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) if (l4d_bit(m1a, m1b, q * 16 + i)) am = fmaxf(am, fabsf(v[i]));
-            }
-            am = block_amax128(am, s_w);
-            const float r = am > 0.f ? pow2_factor(am) : 1.0f;
-            cs2 = cs * r;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float v[16];
-              tmem_ld16(tlane + (uint32_t)(q * 16), v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = l4d_bit(m1a, m1b, q * 16 + i) ? v[i] * r : 0.f;
-              tile_put8(t2h, t2l, tid, 2 * q, v);
-              tile_put8(t2h, t2l, tid, 2 * q + 1, v + 8);
-            }
-          }
-          const float inv2 = 1.0f / cs2;
-          {   // flush dw3 and dW2^T (rows live in lanes < 16 of every warp)
-            float v[16];
-            tmem_ld16(tlane + 176u, v);        // 8 valid columns; column 0 = dw3[row]
-            if (has64) atomicAdd(G.att_w3[net] + row64, v[0] * inv);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              tmem_ld16(tlane + 192u + (uint32_t)(q * 16), v);
-              if (has64) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) atomicAdd(G.att_w2t[net] + (size_t)row64 * 64 + q * 16 + i, v[i] * inv);
-              }
-            }
-          }
-          ms.publish();
-          if (tid == 0) {
-            // dW1g[64 x 16] = dH1^T * [geo,1]
-            mma_tt(tm + 160, aT2h, 64, aG16h, 16, false);
-            mma_tt(tm + 160, aT2l, 64, aG16h, 16, true);
-            mma_tt(tm + 160, aT2h, 64, aG16l, 16, true);
-            // dG[128 x 16] = dH1 * W1g
-            mma_prop(tm + 128, aT2h, 8, sb + L.wa1[net], 64, 16, false);
-            mma_prop(tm + 128, aT2l, 8, sb + L.wa1[net], 64, 16, true);
-            ms.commit();
-          }
-          ms.wait();
-          {
-            float v[16];
-            tmem_ld16(tlane + 128u, v);
-#pragma unroll
-            for (int i = 0; i < 15; ++i) dgeo[i] = fmaf(v[i], inv2, dgeo[i]);
-            tmem_ld16(tlane + 160u, v);
-            if (has64) {
-#pragma unroll
-              for (int i = 0; i < 15; ++i) atomicAdd(G.att_w1t[net] + (size_t)(L4D_ENC + i) * 64 + row64, v[i] * inv2);
-              s_csum[net * 64 + row64] += v[15] * inv2;
-            }
-          }
-          tc_fence_before();
-          __syncthreads();
-          tc_fence_after();
-        }
-      }
-
-      // ---------------- P3: sigma MLP backward ----------------
-      float d16[16];
-      d16[0] = active ? dsigma * expf(fminf(fmaxf(out[0], -15.f), 15.f)) : 0.f;
-#pragma unroll
-      for (int i = 0; i < 15; ++i) d16[1 + i] = active ? dgeo[i] : 0.f;
-      float am = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) am = fmaxf(am, fabsf(d16[i]));
-      const float amax = block_amax128(am, s_w);
-      if (amax == 0.f) {           // nothing flows back through this tile
-        if (active) for (int k = 0; k < (int)M.sigma_in_dim; ++k) A.sv.dfeat[(size_t)k * A.sv.P + p] = 0.f;
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        continue;
-      }
-      const float sc = pow2_factor(amax);
-      float inv = 1.0f / sc;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) d16[i] *= sc;
-      tile_put8(o16h, o16l, tid, 0, d16);
-      tile_put8(o16h, o16l, tid, 1, d16 + 8);
-      ms.publish();
-      if (tid == 0) {
-        // dHs[128 x 64] = dO * W2   (W2 stored [k/8][16 rows][8])
-        mma_prop(tm + 64, aO16h, 2, sb + L.w2, 16, 64, false);
-        mma_prop(tm + 64, aO16l, 2, sb + L.w2, 16, 64, true);
-        // dW2s^T[64 x 16] = Hs^T * dO
-        mma_tt(tm + 144, aHh, 64, aO16h, 16, false);
-        mma_tt(tm + 144, aHl, 64, aO16h, 16, true);
-        mma_tt(tm + 144, aHh, 64, aO16l, 16, true);
-        ms.commit();
-      }
-      ms.wait();
-      {
-        float v[16];
-        tmem_ld16(tlane + 144u, v);
-        if (has64) {
-#pragma unroll
-          for (int o = 0; o < 16; ++o) atomicAdd(G.sig_w2 + (size_t)o * 64 + row64, v[o] * inv);
-        }
-      }
-      {   // re-scale the propagated delta with its own amax, then dHs * relu -> RH (hidden is dead)
-        float am2 = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[16];
-          tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (l4d_bit(msa, msb, q * 16 + i)) am2 = fmaxf(am2, fabsf(v[i]));
-        }
-        am2 = block_amax128(am2, s_w);
-        const float r = am2 > 0.f ? pow2_factor(am2) : 1.0f;
-        inv = 1.0f / (sc * r);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[16];
-          tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = l4d_bit(msa, msb, q * 16 + i) ? v[i] * r : 0.f;
-          tile_put8(hh, hl, tid, 2 * q, v);
-          tile_put8(hh, hl, tid, 2 * q + 1, v + 8);
-        }
-      }
-      // ---------------- P4: input gradients and first-layer weight gradient ----------------
-      load_x(p, active);
-      ms.publish();
-      if (tid == 0) {
-        // dX[128 x in_pad] = dHs * W1   (W1 stored [k/8][64 rows][8])
-        mma_prop(tm + 256, aHh, 8, sb + L.w1, 64, in_pad, false);
-        mma_prop(tm + 256, aHl, 8, sb + L.w1, 64, in_pad, true);
-        // dW1^T[in x 64] = X^T * dHs : rows 0..127, then rows 128..191
-        mma_tt(tm + 192, aXh, 128, aHh, 64, false);
-        mma_tt(tm + 192, aXl, 128, aHh, 64, true);
-        mma_tt(tm + 192, aXh, 128, aHl, 64, true);
-        if (in_pad > 128) {
-          mma_tt(tm + 448, aXh + 16u * 2048u, 64, aHh, 64, false);
-          mma_tt(tm + 448, aXl + 16u * 2048u, 64, aHh, 64, true);
-          mma_tt(tm + 448, aXh + 16u * 2048u, 64, aHl, 64, true);
-        }
-        ms.commit();
-      }
-      ms.wait();
-      for (int q = 0; q < (int)in_pad / 16; ++q) {
-        float v[16];
-        tmem_ld16(tlane + 256u + (uint32_t)(q * 16), v);
-        if (active) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = q * 16 + i;
-            if (k < (int)M.sigma_in_dim) A.sv.dfeat[(size_t)k * A.sv.P + p] = v[i] * inv;
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[16];
-        tmem_ld16(tlane + 192u + (uint32_t)(q * 16), v);
-        if (tid < (int)in_pad) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(G.sig_w1t + (size_t)tid * 64 + q * 16 + i, v[i] * inv);
-        }
-      }
-      if (in_pad > 128) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[16];
-          tmem_ld16(tlane + 448u + (uint32_t)(q * 16), v);
-          if (has64 && 128 + row64 < (int)in_pad) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(G.sig_w1t + (size_t)(128 + row64) * 64 + q * 16 + i, v[i] * inv);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
-    }
-    // direction / ones rows of the first attribute layer: dW1t[k][j] += enc[k] * sum_samples dh1[j]
-    __syncthreads();
-    for (int i = tid; i < 2 * (L4D_ENC + 9) * 64; i += 128) {
-      const int net = i / ((L4D_ENC + 9) * 64);
-      const int r = (i / 64) % (L4D_ENC + 9), jx = i & 63;
-      const float cs = s_csum[net * 64 + jx];
-      if (r < L4D_ENC) atomicAdd(G.att_w1t[net] + (size_t)r * 64 + jx, s_enc[r] * cs);
-      else atomicAdd(G.att_w1t[net] + (size_t)(M.attr_in_dim + (r - L4D_ENC)) * 64 + jx, cs);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 512);
-}
-
-
 namespace l4dtc {
 // 256-thread CTA with two threads per row: warps 0-3 and 4-7 run the same 128-wide scans redundantly
 __device__ __forceinline__ float half_excl_prod(float v, float* s_w, float& total) {
@@ -892,13 +425,20 @@ __device__ __forceinline__ float block_amax256(float v, float* s_w) {
 }
 }  // namespace l4dtc
 
-// Same kernel with 256 threads: two threads per row split the columns of every epilogue (tcgen05.ld lets warps
-// w and w+4 address the same TMEM lane quadrant), which doubles the warps that hide latency (ncu on the
-// 128-thread version: 4 warps/SM, IPC 0.45, stalls on long_scoreboard / wait / instruction fetch).
-__global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ SplitArgs A) {
+#ifdef L4D_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[32];
+#define L4D_PH(i) do { if (tid == 0) { const long long t_ = clock64(); s_clk[i] += (unsigned long long)(t_ - t_last); t_last = t_; } } while (0)
+#else
+#define L4D_PH(i) do { } while (0)
+#endif
+
+// 256 threads, two threads per row that split the columns of every epilogue (tcgen05.ld lets warps w and w+4
+// address the same TMEM lane quadrant): twice the warps to hide latency (a 128-thread, one-thread-per-row
+// version measured 4 warps/SM, IPC 0.45, stalls on long_scoreboard / wait / instruction fetch).
+__global__ void __launch_bounds__(256) k_bwd_dense_tc(const __grid_constant__ SplitArgs A) {
   using namespace l4dtc;
   extern __shared__ __align__(1024) unsigned char dsm[];
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar, s_xbar;
   __shared__ uint32_t s_tmem;
   const DevModel& M = A.M;
   const DevGrads& G = A.G;
@@ -929,8 +469,14 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
   float* s_tstart = s_w + 32;
   __shared__ float s_w3max[2];
   __shared__ float s_part[256];
+#ifdef L4D_PHASE_CLOCKS
+  __shared__ unsigned long long s_clk[32];
+  long long t_last = clock64();
+  if (tid < 32) s_clk[tid] = 0ull;
+  __syncthreads();
+#endif
 
-  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&s_bar, 1); mbar_init(&s_xbar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&s_tmem, 512);
   if (tid < 2) {
     float m = 1.0f;
@@ -961,21 +507,37 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
   const int row64 = wq * 16 + lane;            // row held by this thread in an M=64 accumulator (lanes < 16)
   const bool has64 = lane < 16;
 
-  // features of this thread's sample -> X tile (24 chunks, zero beyond in_pad)
-  auto load_x = [&](size_t p, bool valid) {
-    for (int c0 = 4 * half; c0 < 24; c0 += 8) {      // the two threads of a row interleave groups of 4 chunks
-      float v[4][8];
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = (c0 + cc) * 8 + i;
-          v[cc][i] = (!valid || k >= (int)in_pad) ? 0.f : (k < (int)M.sigma_in_dim ? __ldg(A.sv.feat + (size_t)k * A.sv.P + p) : 1.0f);
-        }
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) tile_put8(xh, xl, row, c0 + cc, v[cc]);
+  // The X tile (fp16 hi|lo operand tile written by k_fwd_gather) arrives by bulk copy.  It is needed twice per tile
+  // (forward recompute, first-layer weight gradient) and the attribute phase reuses its buffer in between, so:
+  //   - the copy for the NEXT tile is issued as soon as this tile's last MMAs have completed (hidden behind the epilogue)
+  //   - the re-load for P4 is issued only if the attribute phase ran, and overlaps with P3
+  const uint32_t xbytes = A.sv.x_chunks * 2048u;
+  uint32_t xphase = 0u;
+  bool x_inflight = false;
+  auto x_issue = [&](uint32_t r, int t) {
+    if (half == 0) {       // tcnn's ones-padding chunks are not stored in global memory
+      for (int c = (int)A.sv.x_chunks; c < 24; ++c) {
+        const bool one = c < n_xchunks;
+        *reinterpret_cast<uint4*>(tile_chunk(xh, row, c)) = one ? make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u) : make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(tile_chunk(xl, row, c)) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
+    if (tid == 0) {
+      const unsigned char* src = A.sv.feat_tc + ((size_t)r * A.sv.n_tiles + (uint32_t)t) * (size_t)(2u * xbytes);
+      mbar_expect_tx(&s_xbar, 2u * xbytes);
+      bulk_g2s(aXh, src, xbytes, &s_xbar);
+      bulk_g2s(aXl, src + xbytes, xbytes, &s_xbar);
+    }
+    x_inflight = true;
   };
+  auto x_wait = [&]() {
+    if (x_inflight) { mbar_wait(&s_xbar, xphase); xphase ^= 1u; x_inflight = false; }
+  };
+  auto x_issue_next = [&](uint32_t r, int t) {       // tiles of a ray are walked back to front
+    if (t > 0) x_issue(r, t - 1);
+    else if (r + gridDim.x < A.n_rays) x_issue(r + gridDim.x, n_tiles - 1);
+  };
+  if (blockIdx.x < A.n_rays) x_issue(blockIdx.x, n_tiles - 1);
 
   for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
     const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
@@ -1012,6 +574,7 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
       }
     }
     __syncthreads();
+    L4D_PH(0);
     float suffix = 0.f;
     for (int t = n_tiles - 1; t >= 0; --t) {
       const uint32_t j = (uint32_t)t * 128 + row;
@@ -1041,9 +604,11 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
         }
       }
 
+      L4D_PH(1);
       // ---------------- P1: sigma MLP forward ----------------
-      load_x(p, active);
+      x_wait();
       ms.publish();
+      L4D_PH(2);
       if (tid == 0) {
         mma_chunks(tm + 0, aXh, sb + L.w1, 64, n_xchunks, false);
         mma_chunks(tm + 0, aXl, sb + L.w1, 64, n_xchunks, true);
@@ -1077,18 +642,24 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
 #pragma unroll
       for (int i = 0; i < 16; ++i) dgeo[i] = 0.f;
 
+      L4D_PH(3);
       // ---------------- P2: attribute heads ----------------
+      bool x_dirty = false;          // the attribute phase reuses the X buffer for its tiles
       if (__syncthreads_or(masked ? 1 : 0)) {
         {   // [geo, 1] tile (zero rows for samples outside the attribute mask)
           float g[16];
 #pragma unroll
           for (int i = 0; i < 15; ++i) g[i] = masked ? out[1 + i] : 0.f;
           g[15] = masked ? 1.0f : 0.f;
-          tile_put8(g16h, g16l, row, half, g + 8 * half);
+          float g8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g8[i] = half ? g[8 + i] : g[i];
+          tile_put8(g16h, g16l, row, half, g8);
         }
 #pragma unroll 1
         for (int net = 0; net < 2; ++net) {
           if (block_amax256(da[net], s_w) == 0.f) continue;       // no gradient reaches this head in this tile
+          x_dirty = true;
           ms.publish();
           if (tid == 0) {
             mma_chunks(tm + 0, aG16h, sb + L.wa1[net], 64, 2, false);
@@ -1203,6 +774,7 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
             }
           }
           const float inv2 = 1.0f / cs2;
+          L4D_PH(4);
           {   // flush dw3 and dW2^T (rows live in lanes < 16 of every warp; columns split between the halves)
             float v[16];
             tmem_ld16(tlane + 176u, v);        // 8 valid columns; column 0 = dw3[row]
@@ -1213,10 +785,12 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
               tmem_ld16(tlane + 192u + (uint32_t)(q * 16), v);
               if (has64) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) atomicAdd(G.att_w2t[net] + (size_t)row64 * 64 + q * 16 + i, v[i] * inv);
+                for (int i = 0; i < 16; i += 4)
+                  l4d_red4(G.att_w2t[net] + (size_t)row64 * 64 + q * 16 + i, v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
               }
             }
           }
+          L4D_PH(5);
           ms.publish();
           if (tid == 0) {
             // dW1g[64 x 16] = dH1^T * [geo,1]
@@ -1239,7 +813,7 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int ii = 8 * half + i;
-                if (ii < 15) atomicAdd(G.att_w1t[net] + (size_t)(L4D_ENC + ii) * 64 + row64, v[ii] * inv2);
+                if (ii < 15) atomicAdd(G.att_w1t[net] + (size_t)(L4D_ENC + ii) * 64 + row64, (half ? v[8 + i] : v[i]) * inv2);
               }
               if (half == 1) s_csum[net * 64 + row64] += v[15] * inv2;
             }
@@ -1247,6 +821,7 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
           tc_fence_before();
           __syncthreads();
           tc_fence_after();
+          L4D_PH(6);
         }
       }
 
@@ -1259,18 +834,26 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
 #pragma unroll
       for (int i = 0; i < 16; ++i) am = fmaxf(am, fabsf(d16[i]));
       const float amax = block_amax256(am, s_w);
+      float* dq = A.sv.dfeat + l4d_dfeat_off(A.sv, ray, j);     // this row in the dfeat tile (float4 per 4 features)
       if (amax == 0.f) {           // nothing flows back through this tile
-        if (active) for (int k = 0; k < (int)M.sigma_in_dim; ++k) A.sv.dfeat[(size_t)k * A.sv.P + p] = 0.f;
+        if (active) for (int kq = half; kq < (int)A.sv.d_quads; kq += 2) *reinterpret_cast<float4*>(dq + (size_t)kq * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        x_issue_next(ray, t);
         continue;
       }
+      if (x_dirty) x_issue(ray, t);      // bring X back for P4 while P3 runs
       const float sc = pow2_factor(amax);
       float inv = 1.0f / sc;
 #pragma unroll
       for (int i = 0; i < 16; ++i) d16[i] *= sc;
-      tile_put8(o16h, o16l, row, half, d16 + 8 * half);
+      {
+        float d8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d8[i] = half ? d16[8 + i] : d16[i];
+        tile_put8(o16h, o16l, row, half, d8);
+      }
       ms.publish();
       if (tid == 0) {
         // dHs[128 x 64] = dO * W2   (W2 stored [k/8][16 rows][8])
@@ -1288,7 +871,7 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
         tmem_ld16(tlane + 144u, v);
         if (has64) {
 #pragma unroll
-          for (int o = 0; o < 8; ++o) atomicAdd(G.sig_w2 + (size_t)(8 * half + o) * 64 + row64, v[8 * half + o] * inv);
+          for (int o = 0; o < 8; ++o) atomicAdd(G.sig_w2 + (size_t)(8 * half + o) * 64 + row64, (half ? v[8 + o] : v[o]) * inv);
         }
       }
       {   // re-scale the propagated delta with its own amax, then dHs * relu -> RH (hidden is dead)
@@ -1315,9 +898,11 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
           tile_put8(hh, hl, row, 2 * q + 1, vv[qq] + 8);
         }
       }
+      L4D_PH(7);
       // ---------------- P4: input gradients and first-layer weight gradient ----------------
-      load_x(p, active);
+      x_wait();
       ms.publish();
+      L4D_PH(8);
       if (tid == 0) {
         // dX[128 x in_pad] = dHs * W1   (W1 stored [k/8][64 rows][8])
         mma_prop(tm + 256, aHh, 8, sb + L.w1, 64, in_pad, false);
@@ -1334,14 +919,17 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
         ms.commit();
       }
       ms.wait();
+      x_issue_next(ray, t);              // X is free: fetch the next tile behind this epilogue
+      L4D_PH(9);
       for (int q = half; q < (int)in_pad / 16; q += 2) {
         float v[16];
         tmem_ld16(tlane + 256u + (uint32_t)(q * 16), v);
         if (active) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = q * 16 + i;
-            if (k < (int)M.sigma_in_dim) A.sv.dfeat[(size_t)k * A.sv.P + p] = v[i] * inv;
+          for (int g = 0; g < 4; ++g) {
+            const int kq = q * 4 + g;
+            if (kq < (int)A.sv.d_quads)
+              *reinterpret_cast<float4*>(dq + (size_t)kq * 512) = make_float4(v[4 * g] * inv, v[4 * g + 1] * inv, v[4 * g + 2] * inv, v[4 * g + 3] * inv);
           }
         }
       }
@@ -1352,7 +940,8 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
         tmem_ld16(tlane + 192u + (uint32_t)(q * 16), v);
         if (row < (int)in_pad) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(G.sig_w1t + (size_t)row * 64 + q * 16 + i, v[i] * inv);
+          for (int i = 0; i < 16; i += 4)
+            l4d_red4(G.sig_w1t + (size_t)row * 64 + q * 16 + i, v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
         }
       }
       if (in_pad > 128) {
@@ -1363,13 +952,15 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
           tmem_ld16(tlane + 448u + (uint32_t)(q * 16), v);
           if (has64 && 128 + row64 < (int)in_pad) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(G.sig_w1t + (size_t)(128 + row64) * 64 + q * 16 + i, v[i] * inv);
+            for (int i = 0; i < 16; i += 4)
+              l4d_red4(G.sig_w1t + (size_t)(128 + row64) * 64 + q * 16 + i, v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
           }
         }
       }
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
+      L4D_PH(11);
     }
     // direction / ones rows of the first attribute layer: dW1t[k][j] += enc[k] * sum_samples dh1[j]
     __syncthreads();
@@ -1383,6 +974,10 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc2(const __grid_constant__ S
   }
   tc_fence_before();
   __syncthreads();
+#ifdef L4D_PHASE_CLOCKS
+  L4D_PH(12);
+  if (tid < 32) atomicAdd(&g_phase_clk[tid], s_clk[tid]);
+#endif
   if (warp == 0) tmem_dealloc(tm, 512);
 }
 

@@ -193,15 +193,19 @@ struct SavedLayout { size_t feat, flow_in, sigma, attr, hidden, flow, dfeat, dfl
 static inline SavedLayout saved_layout(const L4DConfig* c, uint32_t n_rays, uint32_t S) {
   SavedLayout L;
   const size_t P = (size_t)n_rays * S;
+  const size_t tiles = (size_t)n_rays * ((S + 127) / 128);
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-  L.feat = take(P * c->sigma_in_dim * sizeof(float));
+  // features: SoA fp32 planes (fp32-FMA kernels) or fp16 hi|lo operand tiles (tensor-core kernels), same region
+  const size_t feat_soa = P * c->sigma_in_dim * sizeof(float);
+  const size_t feat_tc = tiles * ((c->sigma_in_dim + 7) / 8) * 4096;
+  L.feat = take(feat_soa > feat_tc ? feat_soa : feat_tc);
   L.flow_in = take(P * 16 * sizeof(float));
   L.sigma = take(P * sizeof(float));
   L.attr = take(P * 2 * sizeof(float));
   L.hidden = take((size_t)L4D_BWD_SCRATCH_CTAS * 64 * L4D_NT * sizeof(float));
   L.flow = take(P * 6 * sizeof(float));
-  L.dfeat = take(P * c->sigma_in_dim * sizeof(float));
+  L.dfeat = take(tiles * ((c->sigma_in_dim + 3) / 4) * 2048);
   L.dflow = take(P * 6 * sizeof(float));
   L.total = o;
   return L;
@@ -211,6 +215,10 @@ static inline SavedView saved_view(const L4DConfig* c, void* saved, uint32_t n_r
   char* b = reinterpret_cast<char*>(saved);
   SavedView v;
   v.feat = reinterpret_cast<float*>(b + L.feat);
+  v.feat_tc = reinterpret_cast<unsigned char*>(b + L.feat);
+  v.n_tiles = (S + 127) / 128;
+  v.x_chunks = (c->sigma_in_dim + 7) / 8;
+  v.d_quads = (c->sigma_in_dim + 3) / 4;
   v.flow_in = reinterpret_cast<float*>(b + L.flow_in);
   v.sigma = reinterpret_cast<float*>(b + L.sigma);
   v.attr = reinterpret_cast<float*>(b + L.attr);

@@ -839,6 +839,9 @@ static void fill_split(SplitArgs& A, const L4DConfig* cfg, const void* staged, c
 
 #define L4D_FLAG_FUSED 1u   /* L4DRays.reserved bit 0: single-kernel path */
 
+// the tensor-core dense kernels hold a 128 x sigma_in_pad fp16 hi|lo tile in shared memory: up to 192 inputs (L <= 18)
+static bool use_tc_dense(const L4DConfig* cfg) { return cfg->mlp_fp16 && cfg->sigma_in_pad <= 192; }
+
 extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
                                   float* depth, float* image, float* wsum, float* weights, float* zvals, void* saved,
                                   size_t saved_bytes, void* stream) {
@@ -888,19 +891,26 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
     }
     const size_t smem = 16 * L4D_NT * sizeof(float);
     int grid;
-    rc = grid_for(k_fwd_gather<L4D_NT, true>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
-    if (rc != L4D_OK) return rc;
-    k_fwd_gather<L4D_NT, true><<<grid, L4D_NT, smem, st>>>(A);
+    if (use_tc_dense(cfg)) {
+      const uint32_t work = rays->n_rays * A.sv.n_tiles;       // whole 128-row tiles
+      rc = grid_for(k_fwd_gather<L4D_NT, true, true>, L4D_NT, smem, work, grid);
+      if (rc != L4D_OK) return rc;
+      k_fwd_gather<L4D_NT, true, true><<<grid, L4D_NT, smem, st>>>(A);
+    } else {
+      rc = grid_for(k_fwd_gather<L4D_NT, true, false>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
+      if (rc != L4D_OK) return rc;
+      k_fwd_gather<L4D_NT, true, false><<<grid, L4D_NT, smem, st>>>(A);
+    }
     prof_mark(st, "k_fwd_gather");
   } else {
     const size_t smem = 64 * L4D_NT * sizeof(float);
     int grid;
-    rc = grid_for(k_fwd_gather<L4D_NT, false>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
+    rc = grid_for(k_fwd_gather<L4D_NT, false, false>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
     if (rc != L4D_OK) return rc;
-    k_fwd_gather<L4D_NT, false><<<grid, L4D_NT, smem, st>>>(A);
+    k_fwd_gather<L4D_NT, false, false><<<grid, L4D_NT, smem, st>>>(A);
     prof_mark(st, "k_fwd_gather");
   }
-  if (cfg->mlp_fp16) {
+  if (use_tc_dense(cfg)) {
     const size_t smem = dense_fwd_smem(cfg->sigma_in_pad).total + 1024;
     int grid;
     rc = grid_for(k_fwd_dense_tc, 128, smem, rays->n_rays, grid);
@@ -945,13 +955,12 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
     A.train = 1u;
     const size_t P = (size_t)rays->n_rays * rays->n_steps;
     const uint32_t tiles = (uint32_t)((P + L4D_NT - 1) / L4D_NT);
-    if (cfg->mlp_fp16 && cfg->sigma_in_pad <= 192) {
+    if (use_tc_dense(cfg)) {
       const size_t smem = dense_bwd_smem(cfg->sigma_in_pad).total + 1024;
       int grid;
-      // 256-thread variant (two threads per row); the 128-thread kernel stays as the readable reference version
-      rc = grid_for(k_bwd_dense_tc2, 256, smem, rays->n_rays, grid);
+      rc = grid_for(k_bwd_dense_tc, 256, smem, rays->n_rays, grid);
       if (rc != L4D_OK) return rc;
-      k_bwd_dense_tc2<<<grid, 256, smem, st>>>(A);
+      k_bwd_dense_tc<<<grid, 256, smem, st>>>(A);
       prof_mark(st, "k_bwd_dense_tc");
     } else {
       const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD + 80 + 128 + 128 + 32 + L4D_MAX_TILES) * sizeof(float);
@@ -1126,3 +1135,14 @@ extern "C" int l4d_tc_selftest2(const void* A, const void* B, float* Cout, uint3
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
+
+#ifdef L4D_PHASE_CLOCKS
+// debug build only: per-phase clock sums of k_bwd_dense_tc (thread 0 of every CTA), cleared on read
+extern "C" int l4d_debug_phase_clocks(unsigned long long* out32) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
+  return 0;
+}
+#endif

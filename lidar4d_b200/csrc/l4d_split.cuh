@@ -30,18 +30,29 @@ struct SplitArgs {
 // -------------------------------------------------------------------------------------------
 // forward 1/2: encoders.  thread == sample; writes features, flow-MLP inputs and flow.
 // -------------------------------------------------------------------------------------------
-// FLOW_GIVEN: the flow was already written by k_fwd_flow_tc; then this kernel has no MLP at all
-template <int NT, bool FLOW_GIVEN>
+// FLOW_GIVEN: the flow was already written by k_fwd_flow_tc; then this kernel has no MLP at all.
+// TILE: features go out as the fp16 hi|lo operand tiles of the tensor-core dense kernels (SavedView::feat_tc);
+// the sample space is then walked in whole 128-row tiles so the rows past the end of a ray get zeros.
+template <int NT, bool FLOW_GIVEN, bool TILE>
 __global__ void __launch_bounds__(NT, 4) k_fwd_gather(const __grid_constant__ SplitArgs A) {
   extern __shared__ __align__(16) float smem[];
   float* xb = smem + threadIdx.x;          // exchange column for the flow MLP, stride NT
   const DevModel& M = A.M;
   const size_t P = A.sv.P;
   const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
-  for (size_t base = (size_t)blockIdx.x * NT; base < P; base += (size_t)gridDim.x * NT) {
-    const size_t p = base + threadIdx.x;
-    if (p >= P) continue;
-    const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
+  const uint32_t span = TILE ? A.sv.n_tiles * 128u : A.S;      // index space per ray
+  const size_t PP = (size_t)A.n_rays * span;
+  const uint32_t lo_off = A.sv.x_chunks * 2048u;
+  for (size_t base = (size_t)blockIdx.x * NT; base < PP; base += (size_t)gridDim.x * NT) {
+    const size_t pp = base + threadIdx.x;
+    if (pp >= PP) continue;
+    const uint32_t ray = (uint32_t)(pp / span), j = (uint32_t)(pp % span);
+    unsigned char* tile = TILE ? A.sv.feat_tc + l4d_feat_tc_off(A.sv, ray, j) : nullptr;
+    if (TILE && j >= A.S) {                 // padding row of the last tile of the ray
+      for (uint32_t c = 0; c < 2 * A.sv.x_chunks; ++c) *reinterpret_cast<uint4*>(tile + (size_t)c * 2048) = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    const size_t p = (size_t)ray * A.S + j;
     const float zj = l4d_z(rs, A.ray_offset + ray, j);
     const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
     const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
@@ -59,9 +70,17 @@ __global__ void __launch_bounds__(NT, 4) k_fwd_gather(const __grid_constant__ Sp
       for (int k = 0; k < 6; ++k) A.sv.flow[(size_t)k * P + p] = flow[k];
     }
     FeatSink sink;
-    sink.feat = A.sv.feat; sink.P = P; sink.p = p; sink.dense = nullptr;
+    sink.feat = TILE ? nullptr : A.sv.feat; sink.P = P; sink.p = p; sink.dense = nullptr;
+    sink.tile = tile; sink.tile_lo = lo_off;
     float dummy[L4D_H];
     l4d_gather_features<false>(M, A.F, x, y, z, flow, xb, NT, sink, dummy);
+    if (TILE) {                             // tcnn's ones-padding inside the last stored chunk
+      for (uint32_t k = M.sigma_in_dim; k < A.sv.x_chunks * 8u; ++k) {
+        unsigned char* q = tile + (size_t)(k >> 3) * 2048 + (size_t)(k & 7u) * 2;
+        *reinterpret_cast<__half*>(q) = __float2half_rn(k < M.sigma_in_pad ? 1.0f : 0.f);
+        *reinterpret_cast<__half*>(q + lo_off) = __float2half_rn(0.f);
+      }
+    }
   }
 }
 
@@ -254,8 +273,8 @@ __global__ void __launch_bounds__(NT) k_bwd_dense(const __grid_constant__ SplitA
       }
       // dL/dfeature for the scatter kernel
       if (s.active) {
-        for (int k = 0; k < (int)M.sigma_in_dim; ++k)
-          A.sv.dfeat[(size_t)k * A.sv.P + p] = l4d_dot64(s.dh, M.sig_w1t + (size_t)k * L4D_H);
+        float* dq = A.sv.dfeat + l4d_dfeat_off(A.sv, ray, j);
+        for (int k = 0; k < (int)M.sigma_in_dim; ++k) dq[l4d_dfeat_k(k)] = l4d_dot64(s.dh, M.sig_w1t + (size_t)k * L4D_H);
       }
     }
     for (int i = tid; i < 2 * (L4D_ENC + 9) * 64; i += NT) {
@@ -274,11 +293,10 @@ __global__ void __launch_bounds__(NT) k_bwd_dense(const __grid_constant__ SplitA
 #ifndef L4D_SCATTER_MIN_CTAS
 #define L4D_SCATTER_MIN_CTAS 4
 #endif
-struct DfeatFromPlaneMasked {
-  const float* base;
-  size_t stride;
+struct DfeatFromTile {
+  const float* base;     // this sample's row in its dfeat tile
   bool on;
-  __device__ __forceinline__ float operator()(int row) const { return on ? __ldg(base + (size_t)row * stride) : 0.f; }
+  __device__ __forceinline__ float operator()(int k) const { return on ? __ldg(base + l4d_dfeat_k(k)) : 0.f; }
 };
 
 template <int NT>
@@ -300,8 +318,8 @@ __global__ void __launch_bounds__(NT, L4D_SCATTER_MIN_CTAS) k_bwd_scatter(const 
     float flow[6], dflow[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) flow[k] = A.sv.flow[(size_t)k * P + p];
-    DfeatFromPlaneMasked df{A.sv.dfeat + p, P, active};
-    l4d_bw_scatter_t<true, DfeatFromPlaneMasked, false>(M, A.F, A.G, x, y, z, flow, df, dflow, active);
+    DfeatFromTile df{A.sv.dfeat + l4d_dfeat_off(A.sv, ray, j), active};
+    l4d_bw_scatter_t<true, DfeatFromTile, false>(M, A.F, A.G, x, y, z, flow, df, dflow, active);
     if (active) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) A.sv.dflow[(size_t)k * P + p] = dflow[k];
@@ -425,10 +443,11 @@ __global__ void __launch_bounds__(NT, 8) k_bwd_scatter_static(const __grid_const
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
     float* gbase = A.G.hs + (size_t)M.gs.offset[l] * 4;
-    const float* d = A.sv.dfeat + (size_t)(row_hash_s + 4 * l) * P;
+    const size_t dk = l4d_dfeat_k(row_hash_s + 4 * l);     // row_hash_s is a multiple of 16: one float4 per level
     for (size_t p = (size_t)blockIdx.x * NT + threadIdx.x; p < P; p += (size_t)gridDim.x * NT) {
-      const float d0 = __ldg(d + p), d1 = __ldg(d + P + p), d2 = __ldg(d + 2 * P + p), d3 = __ldg(d + 3 * P + p);
       const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
+      const float4 dd = __ldg(reinterpret_cast<const float4*>(A.sv.dfeat + l4d_dfeat_off(A.sv, ray, j) + dk));
+      const float d0 = dd.x, d1 = dd.y, d2 = dd.z, d3 = dd.w;
       const float zj = l4d_z(rs, A.ray_offset + ray, j);
       const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
       const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
