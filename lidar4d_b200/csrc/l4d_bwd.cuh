@@ -369,6 +369,7 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
     const float ca = p == 2 ? y : x, cb = p == 0 ? y : z;
     float* glo = G.hd[p][F.cur.slice_lo];
     float* ghi = G.hd[p][F.cur.slice_hi];
+    float* gcomb = G.hd_comb[p];
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
       uint32_t idx[4]; float w[4];
@@ -377,6 +378,11 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
       const float e0 = d * F.cur.basis[0], e1 = d * F.cur.basis[1], e2 = d * F.cur.basis[2], e3 = d * F.cur.basis[3];
       const float slo = F.cur.single ? 1.0f : F.cur.w_lo;
       const size_t off = (size_t)M.gd[p].offset[l] * 4;
+      if (gcomb) {          // slice weights are applied by k_fold_dynamic
+#pragma unroll
+        for (int c = 0; c < 4; ++c) l4d_red4(gcomb + off + (size_t)idx[c] * 4, w[c] * e0, w[c] * e1, w[c] * e2, w[c] * e3);
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float ww = w[c] * slo;

@@ -82,6 +82,11 @@ struct DevGrads {
   float* hs;                                   // [entries][4] fp32
   float* hd[3][L4D_MAX_TIME_SLICES];           // per slice [entries][4]
   float* hf;                                   // [entries][8]
+  // optional work accumulators (split pipeline): every sample of a launch shares the frame, hence the time-slice
+  // weights and the Lagrange basis, so the scatter kernels reduce the slice- / basis-independent part once per corner
+  // and k_fold_* distributes it afterwards: half the reductions.
+  float* hd_comb[3];                           // [entries][4]  sum of w_corner * d * basis[0..4) (before the slice weights)
+  float* hf_comb;                              // [entries][2]  sum of w_corner * dFin[2l + c]   (before the basis)
   float* planes_cl[L4D_MAX_PLANE_SCALES][6];   // channels-last work grads
   float *sig_w1t, *sig_w2;                     // [in_pad][64], [16][64]
   float *att_w1t[2], *att_w2t[2], *att_w3[2];  // [96][64], [64][64], [64]

@@ -987,7 +987,7 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc(const __grid_constant__ Sp
 struct FlowTcSmem {
   uint32_t w0, w1, w2;       // weights
   uint32_t fin;              // 16-wide tile hi|lo (2 x 4 KB)
-  uint32_t t1, t2, t3;       // 64-wide tiles hi|lo (32 KB each); the forward uses t1 only
+  uint32_t t1, t2;           // 64-wide tiles hi|lo (32 KB each); the forward uses t1 only
   uint32_t do16;             // 16-wide delta tile hi|lo
   uint32_t total_fwd, total;
 };
@@ -999,7 +999,7 @@ __host__ __device__ inline FlowTcSmem flow_tc_smem() {
   L.fin = take(2 * 4096);
   L.t1 = take(32 * 1024);
   L.total_fwd = o;
-  L.t2 = take(32 * 1024); L.t3 = take(32 * 1024);
+  L.t2 = take(32 * 1024);
   L.do16 = take(2 * 4096);
   L.total = o;
   return L;
@@ -1152,6 +1152,8 @@ __global__ void __launch_bounds__(128, 4) k_fwd_flow_tc(const __grid_constant__ 
 // -------------------------------------------------------------------------------------------
 // backward 3/4 on tensor cores: flow MLP backprop + weight gradients; dL/d(flow-MLP input) -> flow_in planes
 // TMEM (256 cols): [0,64) [64,128) work, [128,144) dW2^T, [144,160) dW0, [192,256) dW1^T
+// Two 64-wide tiles are enough (each delta tile overwrites the activation tile that has just been consumed), which
+// keeps the CTA at 92 KB of shared memory and 256 TMEM columns: two CTAs per SM overlap each other's MMA round trips.
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ SplitArgs A) {
   using namespace l4dtc;
@@ -1164,10 +1166,10 @@ __global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ Spl
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const FlowTcSmem L = flow_tc_smem();
   const uint32_t sb = smem_u32(dsm);
-  unsigned char *t2h = dsm + L.t2, *t2l = t2h + 16384, *t3h = dsm + L.t3, *t3l = t3h + 16384;
+  unsigned char *t1h = dsm + L.t1, *t1l = t1h + 16384, *t2h = dsm + L.t2, *t2l = t2h + 16384;
   unsigned char *o16h = dsm + L.do16, *o16l = o16h + 4096;
   const uint32_t aFinH = sb + L.fin, aFinL = aFinH + 4096u;
-  const uint32_t aT1h = sb + L.t1, aT1l = aT1h + 16384u, aT2h = sb + L.t2, aT2l = aT2h + 16384u, aT3h = sb + L.t3, aT3l = aT3h + 16384u;
+  const uint32_t aT1h = sb + L.t1, aT1l = aT1h + 16384u, aT2h = sb + L.t2, aT2l = aT2h + 16384u;
   const uint32_t aO16h = sb + L.do16, aO16l = aO16h + 4096u;
   if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&s_tmem, 256);
@@ -1230,7 +1232,7 @@ __global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ Spl
       }
     }
     float cs2;
-    {   // dH2 * relu2, re-scaled -> T3
+    {   // dH2 * relu2, re-scaled -> T1 (H2 is dead: dW2^T has been computed)
       float a2 = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -1248,19 +1250,19 @@ __global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ Spl
         tmem_ld16(tlane + (uint32_t)(q * 16), v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = l4d_bit(m2a, m2b, q * 16 + i) ? v[i] * r : 0.f;
-        tile_put8(t3h, t3l, tid, 2 * q, v);
-        tile_put8(t3h, t3l, tid, 2 * q + 1, v + 8);
+        tile_put8(t1h, t1l, tid, 2 * q, v);
+        tile_put8(t1h, t1l, tid, 2 * q + 1, v + 8);
       }
     }
     inv = 1.0f / cs2;
     ms.publish();
     if (tid == 0) {
       // dH1[128 x 64] = dH2 * W1 ; dW1^T[64 x 64] = H1^T * dH2
-      mma_prop(tm + 64, aT3h, 8, sb + L.w1, 64, 64, false);
-      mma_prop(tm + 64, aT3l, 8, sb + L.w1, 64, 64, true);
-      mma_tt(tm + 192, aT2h, 64, aT3h, 64, false);
-      mma_tt(tm + 192, aT2l, 64, aT3h, 64, true);
-      mma_tt(tm + 192, aT2h, 64, aT3l, 64, true);
+      mma_prop(tm + 64, aT1h, 8, sb + L.w1, 64, 64, false);
+      mma_prop(tm + 64, aT1l, 8, sb + L.w1, 64, 64, true);
+      mma_tt(tm + 192, aT2h, 64, aT1h, 64, false);
+      mma_tt(tm + 192, aT2l, 64, aT1h, 64, true);
+      mma_tt(tm + 192, aT2h, 64, aT1l, 64, true);
       ms.commit();
     }
     ms.wait();
@@ -1270,12 +1272,12 @@ __global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ Spl
       tmem_ld16(tlane + 192u + (uint32_t)(q * 16), v);
       if (has64) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(G.flo_w1t + (size_t)row64 * 64 + q * 16 + i, v[i] * inv);
+        for (int i = 0; i < 16; i += 4)
+          l4d_red4(G.flo_w1t + (size_t)row64 * 64 + q * 16 + i, v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
       }
     }
     float cs3;
-    {   // dH1 * relu1, re-scaled -> T1 (H2 is dead)
-      unsigned char *t1h = dsm + L.t1, *t1l = t1h + 16384;
+    {   // dH1 * relu1, re-scaled -> T2 (H1 is dead: dW1^T has been computed)
       float a3 = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -1293,19 +1295,19 @@ __global__ void __launch_bounds__(128) k_bwd_flow_tc(const __grid_constant__ Spl
         tmem_ld16(tlane + 64u + (uint32_t)(q * 16), v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = l4d_bit(m1a, m1b, q * 16 + i) ? v[i] * r : 0.f;
-        tile_put8(t1h, t1l, tid, 2 * q, v);
-        tile_put8(t1h, t1l, tid, 2 * q + 1, v + 8);
+        tile_put8(t2h, t2l, tid, 2 * q, v);
+        tile_put8(t2h, t2l, tid, 2 * q + 1, v + 8);
       }
     }
     inv = 1.0f / cs3;
     ms.publish();
     if (tid == 0) {
       // dFin[128 x 16] = dH1 * W0 ; dW0[64 x 16] = dH1^T * Fin
-      mma_prop(tm + 0, aT1h, 8, sb + L.w0, 64, 16, false);
-      mma_prop(tm + 0, aT1l, 8, sb + L.w0, 64, 16, true);
-      mma_tt(tm + 144, aT1h, 64, aFinH, 16, false);
-      mma_tt(tm + 144, aT1l, 64, aFinH, 16, true);
-      mma_tt(tm + 144, aT1h, 64, aFinL, 16, true);
+      mma_prop(tm + 0, aT2h, 8, sb + L.w0, 64, 16, false);
+      mma_prop(tm + 0, aT2l, 8, sb + L.w0, 64, 16, true);
+      mma_tt(tm + 144, aT2h, 64, aFinH, 16, false);
+      mma_tt(tm + 144, aT2l, 64, aFinH, 16, true);
+      mma_tt(tm + 144, aT2h, 64, aFinL, 16, true);
       ms.commit();
     }
     ms.wait();

@@ -23,6 +23,7 @@ struct GradWorkLayout {
   size_t sig_w1t, sig_w2;
   size_t att_w1t[2], att_w2t[2], att_w3[2];
   size_t flo_w0t, flo_w1t, flo_w2;
+  size_t hd_comb[3], hf_comb;
   size_t total;
 };
 
@@ -95,6 +96,8 @@ static inline GradWorkLayout grad_work_layout(const L4DConfig* c) {
   L.flo_w0t = take(16 * 64 * f);
   L.flo_w1t = take(64 * 64 * f);
   L.flo_w2 = take(8 * 64 * f);
+  for (int p = 0; p < 3; ++p) L.hd_comb[p] = take((size_t)c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels] * 4 * f);
+  L.hf_comb = take((size_t)c->flow.offset[c->flow.n_levels] * 2 * f);
   L.total = o;
   return L;
 }
@@ -170,7 +173,7 @@ static inline void build_model(const L4DConfig* c, const void* staged, DevModel&
   M.density_scale = c->density_scale;
 }
 
-static inline void build_grads(const L4DConfig* c, const L4DMasterGrads* g, void* grad_work, DevGrads& G) {
+static inline void build_grads(const L4DConfig* c, const L4DMasterGrads* g, void* grad_work, DevGrads& G, bool comb = false) {
   GradWorkLayout L = grad_work_layout(c);
   char* b = reinterpret_cast<char*>(grad_work);
   memset(&G, 0, sizeof(G));
@@ -184,6 +187,10 @@ static inline void build_grads(const L4DConfig* c, const L4DMasterGrads* g, void
   G.sig_w1t = F(L.sig_w1t); G.sig_w2 = F(L.sig_w2);
   for (int n = 0; n < 2; ++n) { G.att_w1t[n] = F(L.att_w1t[n]); G.att_w2t[n] = F(L.att_w2t[n]); G.att_w3[n] = F(L.att_w3[n]); }
   G.flo_w0t = F(L.flo_w0t); G.flo_w1t = F(L.flo_w1t); G.flo_w2 = F(L.flo_w2);
+  if (comb) {
+    for (int p = 0; p < 3; ++p) G.hd_comb[p] = F(L.hd_comb[p]);
+    G.hf_comb = F(L.hf_comb);
+  }
 }
 
 

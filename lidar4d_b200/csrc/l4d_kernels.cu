@@ -132,6 +132,36 @@ __global__ void k_add(const float* __restrict__ src, float* __restrict__ dst, in
   if (i < n) dst[i] += src[i];
 }
 
+// distribute the slice-independent dynamic-hash gradient over the two live time slices and clear it (DevGrads::hd_comb)
+__global__ void k_fold_dynamic(float4* __restrict__ comb, float4* __restrict__ glo, float4* __restrict__ ghi, size_t n,
+                               float w_lo, float w_hi) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 c = comb[i];
+  if (c.x == 0.f && c.y == 0.f && c.z == 0.f && c.w == 0.f) return;
+  float4 a = glo[i];
+  a.x = fmaf(w_lo, c.x, a.x); a.y = fmaf(w_lo, c.y, a.y); a.z = fmaf(w_lo, c.z, a.z); a.w = fmaf(w_lo, c.w, a.w);
+  glo[i] = a;
+  if (ghi) {
+    float4 b = ghi[i];
+    b.x = fmaf(w_hi, c.x, b.x); b.y = fmaf(w_hi, c.y, b.y); b.z = fmaf(w_hi, c.z, b.z); b.w = fmaf(w_hi, c.w, b.w);
+    ghi[i] = b;
+  }
+  comb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// flow grid: feature (2i + c) of an entry gets basis[i] * comb[entry][c] (DevGrads::hf_comb), then clear
+__global__ void k_fold_flow(float2* __restrict__ comb, float4* __restrict__ g, size_t n, float b0, float b1, float b2, float b3) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 c = comb[i];
+  if (c.x == 0.f && c.y == 0.f) return;
+  float4 lo = g[2 * i], hi = g[2 * i + 1];
+  lo.x = fmaf(b0, c.x, lo.x); lo.y = fmaf(b0, c.y, lo.y); lo.z = fmaf(b1, c.x, lo.z); lo.w = fmaf(b1, c.y, lo.w);
+  hi.x = fmaf(b2, c.x, hi.x); hi.y = fmaf(b2, c.y, hi.y); hi.z = fmaf(b3, c.x, hi.z); hi.w = fmaf(b3, c.y, hi.w);
+  g[2 * i] = lo; g[2 * i + 1] = hi;
+  comb[i] = make_float2(0.f, 0.f);
+}
+
 // round fp32 values to the nearest fp16-representable value (MLP weights in mlp_fp16 mode)
 __global__ void k_round_fp16(float* __restrict__ w, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -950,7 +980,7 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
   if (!(rays->reserved & L4D_FLAG_FUSED)) {
     SplitArgs A;
     fill_split(A, cfg, staged, frame, rays, const_cast<void*>(saved));
-    build_grads(cfg, grads, grad_work, A.G);
+    build_grads(cfg, grads, grad_work, A.G, true);
     A.g_depth = g_depth; A.g_image = g_image; A.g_wsum = g_wsum; A.g_weights = g_weights;
     A.train = 1u;
     const size_t P = (size_t)rays->n_rays * rays->n_steps;
@@ -981,18 +1011,30 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
       if (rc != L4D_OK) return rc;
       k_bwd_scatter_static<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
       prof_mark(st, "k_bwd_scatter_static");
+      for (int p = 0; p < 3; ++p) {
+        const size_t n = cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels];
+        const bool single = frame->cur.single != 0;
+        k_fold_dynamic<<<nblk(n), 256, 0, st>>>(reinterpret_cast<float4*>(A.G.hd_comb[p]),
+                                               reinterpret_cast<float4*>(A.G.hd[p][frame->cur.slice_lo]),
+                                               single ? nullptr : reinterpret_cast<float4*>(A.G.hd[p][frame->cur.slice_hi]), n,
+                                               single ? 1.0f : frame->cur.w_lo, frame->cur.w_hi);
+      }
+      prof_mark(st, "k_fold_dynamic");
     }
     if (frame->has_fwd || frame->has_bwd) {     // with no neighbour frame nothing reaches the flow field
       if (cfg->mlp_fp16) {
         const size_t smem = flow_tc_smem().total + 1024;
         int grid;
-        rc = grid_for(k_bwd_flow_tc, 128, smem, tiles, grid);
+        rc = grid_for(k_bwd_flow_tc, 128, smem, tiles, grid, 2);     // 92 KB + 256 TMEM columns: two per SM
         if (rc != L4D_OK) return rc;
         k_bwd_flow_tc<<<grid, 128, smem, st>>>(A);
         prof_mark(st, "k_bwd_flow_tc");
         rc = grid_for(k_bwd_flowgrid<L4D_NT>, L4D_NT, 0, tiles, grid);
         if (rc != L4D_OK) return rc;
         k_bwd_flowgrid<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
+        const size_t n = cfg->flow.offset[cfg->flow.n_levels];
+        const float* fb = frame->flow_basis;
+        k_fold_flow<<<nblk(n), 256, 0, st>>>(reinterpret_cast<float2*>(A.G.hf_comb), reinterpret_cast<float4*>(A.G.hf), n, fb[0], fb[1], fb[2], fb[3]);
         prof_mark(st, "k_bwd_flowgrid");
       } else {
         const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD) * sizeof(float);

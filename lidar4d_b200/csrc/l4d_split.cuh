@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(NT, 4) k_bwd_flowgrid(const __grid_constant__ 
       uint32_t idx[8]; float w[8];
       l4d_corners3(M.gf, l, x, y, z, idx, w);
       float* gb = A.G.hf + (size_t)M.gf.offset[l] * 8;
+      float* gc = A.G.hf_comb ? A.G.hf_comb + (size_t)M.gf.offset[l] * 2 : nullptr;    // basis applied by k_fold_flow
       if (M.gf.res[l] <= 400u) {            // warp-uniform: aggregate runs of equal cells
         uint32_t cx, cy, cz; float fx, fy, fz;
         const float sc = M.gf.scale[l];
@@ -409,12 +410,17 @@ __global__ void __launch_bounds__(NT, 4) k_bwd_flowgrid(const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float s0 = l4d_seg_sum(w[c] * d0, r.dist), s1 = l4d_seg_sum(w[c] * d1, r.dist);
-          if (r.tail) {
+          if (r.tail && gc) {
+            atomicAdd(reinterpret_cast<float2*>(gc + (size_t)idx[c] * 2), make_float2(s0, s1));
+          } else if (r.tail) {
             float* q = gb + (size_t)idx[c] * 8;
             l4d_red4(q, b[0] * s0, b[0] * s1, b[1] * s0, b[1] * s1);
             l4d_red4(q + 4, b[2] * s0, b[2] * s1, b[3] * s0, b[3] * s1);
           }
         }
+      } else if (active && gc) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) atomicAdd(reinterpret_cast<float2*>(gc + (size_t)idx[c] * 2), make_float2(w[c] * d0, w[c] * d1));
       } else if (active) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {

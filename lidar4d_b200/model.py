@@ -282,7 +282,7 @@ class _RenderFn(torch.autograd.Function):
             _capi.check(lib, rc, "l4d_render_backward")
             rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), nwork, C.byref(tab), eng.stream())
             _capi.check(lib, rc, "l4d_unstage_grads")
-        eng.n_launches += (1 if ctx.fused else (5 if eng.mlp_fp16 else 4)) + 6 * eng.cfg.n_levels_plane + 11
+        eng.n_launches += (1 if ctx.fused else (9 if eng.mlp_fp16 else 7)) + 6 * eng.cfg.n_levels_plane + 11
         eng.owner._last_grad_arena = flat
         ctx.saved = None
         return (None,) * 10 + tuple(views[n] for n in eng.names)
