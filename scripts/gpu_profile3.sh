@@ -5,6 +5,6 @@ ARGS="--steps 1 --warmup 1 --rays 8192 --ray-batch 8192 --no-cpu-baseline"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv \
     python bench.py $ARGS > gpurun_out/ncu_launch_run.log 2>&1
 echo "launch list rc=$?"
-timeout 2400 ncu --set full --clock-control none --import-source on -k regex:"k_fwd_|k_bwd_" -s 8 -c 8 -f -o gpurun_out/prof \
+timeout 2400 ncu --set full --clock-control none --import-source on -k regex:"k_fwd_|k_bwd_|k_fold_" -s 13 -c 13 -f -o gpurun_out/prof \
     python bench.py $ARGS > gpurun_out/ncu_full_run.log 2>&1
 echo "full capture rc=$?"; ls -la gpurun_out/*.ncu-rep; grep -E "passes|Profiling" gpurun_out/ncu_full_run.log | head -12

@@ -46,6 +46,18 @@ if os.path.exists(rep):
             "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
     kn = idx["Kernel Name"]
+    # dram bytes per launch of every kernel -> profiles/ncu_traffic.json (bench.py's roofline.traffic)
+    import json
+    traffic = {}
+    for r in rows[2:]:
+        name = re.sub(r"[<(].*", "", r[kn]).replace("void ", "").strip()
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[idx[m]]]
+            tot += float(r[idx[m]].replace(",", "")) * mult
+        traffic.setdefault(name, tot)
+    json.dump({"source": f"{tag}_ncu_summary.md", "config": "L=16, 8192 rays x 768 samples per launch", "dram_bytes_per_launch": traffic},
+              open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
     out.append("## `ncu --set full --clock-control none --import-source on` capture (per launch)\n")
     out.append("| metric | " + " | ".join(re.sub(r"\(.*", "", r[kn]) for r in rows[2:]) + " | unit |")
     out.append("|---|" + "---|" * (len(rows) - 1))
