@@ -370,6 +370,29 @@ def run_b200(args):
     ktimes = _capi.profile_kernels(lambda: [step(args.warmup + i, False) for i in range(2)])
     torch.cuda.synchronize()
 
+    # ---- the two density regimes and their measured attribute-mask fraction M/P ----
+    def mask_fraction():
+        keep = model.materialize_weights
+        model.materialize_weights = True
+        with torch.no_grad():
+            ro_h, rd_h, t = frames[0]
+            sel = torch.linspace(0, n_rays - 1, min(1024, n_rays)).long()
+            out = model.render(ro_h[sel].to(dev)[None], rd_h[sel].to(dev)[None], t, staged=False, num_steps=S_STEPS, perturb=False)
+            mf = float((out["weights"] > 1e-4).float().mean())
+        model.materialize_weights = keep
+        return mf
+
+    regimes = {"init-like": {"mask_fraction": mask_fraction(), "rays_per_s": n_rays * world * args.steps / (ms * 1e-3)}}
+    with torch.no_grad():           # surface-like: positive, scaled sigma row => the weight mass sits in a few samples per ray
+        pz = model.sigma_net.params
+        off = 64 * model.cfg.sigma_in_pad
+        pz[off:off + 64] = pz[off:off + 64].abs() * 4.0
+    model._engine.ensure_staged()
+    step(0, False)
+    ms_s, _ = timed(False, 2, 1)
+    regimes["surface-like"] = {"mask_fraction": mask_fraction(), "rays_per_s": n_rays * world * 2 / (ms_s * 1e-3)}
+    log(f"regimes: {regimes}")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -413,7 +436,7 @@ def run_b200(args):
         "config": workload_config(args),
         "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n_rays * 6 * 4,
                 "d2h_bytes_per_step": n_rays * 3 * 4 + 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "regimes": regimes,
     }
     log(f"e2e {ms_e2e / args.steps:.1f} ms/step; kernels " + ", ".join(f"{k} {v['avg_ms']:.2f} ms" for k, v in kern.items()))
     if not args.no_cpu_baseline and world == 1:

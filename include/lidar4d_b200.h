@@ -196,6 +196,11 @@ int    l4d_density_forward(const L4DConfig* cfg, const void* staged, const L4DFr
                            const float* x, uint32_t n, float* sigma, float* geo,
                            float* features_or_null, float* flow_or_null, void* stream);
 
+/* LiDAR4D.attribute (lidar4d.py:191-223) on explicit points: unit directions d[n,3], geo_feat[n,15],
+ * optional mask[n] (uint8, 0 = row stays zero) -> out[n,2] = (raydrop, intensity) after the sigmoid. */
+int    l4d_attribute_forward(const L4DConfig* cfg, const void* staged, const float* d, const float* geo,
+                             const unsigned char* mask_or_null, uint32_t n, float* out, void* stream);
+
 /* --- profiling aid: while started, CUDA events are recorded on the launch stream around every kernel of
  *     l4d_render_forward / l4d_render_backward.  l4d_profile_stop returns the number of (kernel name, ms)
  *     pairs written (static strings), or a negative error code.  Not thread-safe. --------------------------- */

@@ -812,6 +812,41 @@ __global__ void __launch_bounds__(NT) k_density(const __grid_constant__ DensityA
   if (A.flow) for (int k = 0; k < 6; ++k) A.flow[(size_t)i * 6 + k] = fl[k];
 }
 
+// LiDAR4D.attribute on explicit points (parity / API completeness; render() has the heads fused in)
+struct AttributeArgs {
+  DevModel M;
+  const float* d;
+  const float* geo;
+  const unsigned char* mask;
+  uint32_t n;
+  float* out;
+};
+template <int NT>
+__global__ void __launch_bounds__(NT) k_attribute(const __grid_constant__ AttributeArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float* xb = smem + threadIdx.x;                    // exchange column, stride NT
+  float* enc = smem + 64 * NT + threadIdx.x * 81;    // this point's direction encoding (odd stride: conflict-free)
+  float* cdir = smem + 64 * NT + 81 * NT + threadIdx.x * 129;
+  const DevModel& M = A.M;
+  const uint32_t i = blockIdx.x * NT + threadIdx.x;
+  if (i >= A.n) return;
+  float o0 = 0.f, o1 = 0.f;
+  if (!A.mask || A.mask[i]) {
+    const float dx = A.d[3 * i], dy = A.d[3 * i + 1], dz = A.d[3 * i + 2];
+    for (int k = 0; k < L4D_ENC; ++k) {
+      const int dim = k / 24, f = (k % 24) >> 1, ph = k & 1;
+      enc[k] = l4d_freq(dim == 0 ? dx : (dim == 1 ? dy : dz), f, ph);
+    }
+    for (int k = 0; k < 128; ++k) cdir[k] = l4d_attr_cdir(M, k >> 6, k & 63, enc);
+    float geo[L4D_GEO];
+    for (int k = 0; k < L4D_GEO; ++k) geo[k] = A.geo[(size_t)i * L4D_GEO + k];
+    o0 = l4d_attr_net(M, 0, cdir, geo, xb, NT);
+    o1 = l4d_attr_net(M, 1, cdir, geo, xb, NT);
+  }
+  A.out[2 * i] = o0;
+  A.out[2 * i + 1] = o1;
+}
+
 // =============================================================================
 // C-ABI launchers
 // =============================================================================
@@ -1147,6 +1182,24 @@ extern "C" int l4d_density_forward(const L4DConfig* cfg, const void* staged, con
   const size_t smem = 64 * L4D_NT * sizeof(float);
   L4D_CUDA(cudaFuncSetAttribute(k_density<L4D_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_density<L4D_NT><<<nblk(n, L4D_NT), L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+extern "C" int l4d_attribute_forward(const L4DConfig* cfg, const void* staged, const float* d, const float* geo,
+                                     const unsigned char* mask, uint32_t n, float* out, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  if (!staged || !d || !geo || !out) return l4d_fail(L4D_EINVAL, "null pointer");
+  if (n == 0) return L4D_OK;
+  AttributeArgs A;
+  memset(&A, 0, sizeof(A));
+  build_model(cfg, staged, A.M);
+  A.d = d; A.geo = geo; A.mask = mask; A.n = n; A.out = out;
+  constexpr int NT = 64;
+  const size_t smem = (size_t)(64 + 81 + 129) * NT * sizeof(float);
+  L4D_CUDA(cudaFuncSetAttribute(k_attribute<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_attribute<NT><<<nblk(n, NT), NT, smem, (cudaStream_t)stream>>>(A);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }

@@ -494,8 +494,26 @@ class LiDAR4D(LiDAR_Renderer):
             out.update(features=feats, flow=flow)
         return out
 
+    # ---- LiDAR4D.attribute (lidar4d.py:191-223), inference / parity only; render() has the heads fused in ----
+    @torch.no_grad()
     def attribute(self, x, d, mask=None, geo_feat=None, **kwargs):
-        raise NotImplementedError("attribute heads are fused into render()/run(); see lidar4d_b200/csrc/l4d_core.cuh")
+        """x is unused (as in the reference); d [N,3] unit directions, geo_feat [N,15], mask [N] bool or None.
+        Returns [N,2] = (raydrop, intensity); rows outside the mask are zero."""
+        eng = self._engine
+        lib = eng._lib()
+        d = d.detach().contiguous().view(-1, 3).float()
+        eng._require_cuda(d)
+        eng.ensure_staged()
+        n = d.shape[0]
+        geo = geo_feat.detach().contiguous().view(n, 15).float()
+        m8 = None if mask is None else mask.detach().contiguous().view(n).to(torch.uint8)
+        out = torch.empty(n, self.out_lidar_dim, device=d.device)
+        with torch.cuda.device(d.device):
+            rc = lib.l4d_attribute_forward(C.byref(eng.ccfg), eng.staged.data_ptr(), d.data_ptr(), geo.data_ptr(),
+                                           m8.data_ptr() if m8 is not None else None, n, out.data_ptr(), eng.stream())
+        _capi.check(lib, rc, "l4d_attribute_forward")
+        eng.n_launches += 1
+        return out
 
     @torch.no_grad()
     def hash_indices(self, grid_id: int, level: int, x: torch.Tensor):

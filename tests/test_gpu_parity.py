@@ -137,6 +137,27 @@ def test_flow_forward_backward(dev):
         assert rel_err(dict(m.named_parameters())[k].grad, og[k]) < TOL, k
 
 
+@pytest.mark.parametrize("fp16", [False, True])
+def test_attribute_heads_standalone(dev, fp16):
+    """LiDAR4D.attribute (lidar4d.py:191-223) on explicit directions / geo features, with and without a mask."""
+    orc = O.build_seeded(small_config(), 14)
+    if fp16:
+        orc.mlp_dtype = "fp16"
+    m = cuda_model_from_oracle(orc).set_mlp_fp16(fp16)
+    g = torch.Generator().manual_seed(2)
+    n = 301
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    geo = torch.randn(n, 15, generator=g)
+    mask = torch.rand(n, generator=g) > 0.4
+    for mk in (None, mask, torch.zeros(n, dtype=torch.bool)):
+        ref = orc.attribute(d, geo, mk)
+        got = m.attribute(None, d.to(dev), None if mk is None else mk.to(dev), geo.to(dev))
+        assert got.shape == (n, 2)
+        assert float((got.cpu() - ref).abs().max()) < 1e-5
+        if mk is not None:
+            assert float(got.cpu()[~mk].abs().max() if (~mk).any() else 0.0) == 0.0
+
+
 def test_staged_render_and_empty_mask(dev):
     orc = O.build_seeded(small_config(), 9)
     c = orc.cfg
@@ -268,11 +289,17 @@ def test_tcgen05_selftest_gemm(dev, N, K):
 TC_CASES = [(0.4, 200, False, 3, False), (0.0, 150, True, 4, False), (0.6, 260, True, 6, True), (0.4, 768, True, 27, False)]
 
 
-@pytest.mark.parametrize("t,S,perturb,seed,surface", TC_CASES)
-def test_tensor_core_path(dev, t, S, perturb, seed, surface):
+# odd level counts: sigma_in_dim = 85 / 99 is not a multiple of 4 or 8, so the feature-tile writer takes its scalar path,
+# the last stored 16-byte chunk is partly ones-padding and the last dfeat float4 is partly unused
+TC_CASES += [(0.4, 140, True, 11, False, 3), (0.4, 140, True, 11, False, 5)]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tensor_core_path(dev, case):
     """mlp_fp16 mode: the dense kernels run on tcgen05 tensor cores (fp16 hi/lo-split activations, fp16 weights,
     fp32 TMEM accumulation).  The oracle emulates the fp16 weight rounding exactly; tolerance stays 1e-4."""
-    orc = O.build_seeded(small_config(), seed, flow_last_std=0.02)
+    t, S, perturb, seed, surface = case[:5]
+    orc = O.build_seeded(small_config(**({"n_levels_hash": case[5]} if len(case) > 5 else {})), seed, flow_last_std=0.02)
     if surface:
         make_surface_like(orc)
     orc.mlp_dtype = "fp16"
