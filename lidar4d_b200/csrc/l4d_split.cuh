@@ -290,8 +290,10 @@ __global__ void __launch_bounds__(NT) k_bwd_dense(const __grid_constant__ SplitA
 // -------------------------------------------------------------------------------------------
 // backward 2/3: scatter dL/dfeature through the encoders (vector REDs), thread == sample.
 // -------------------------------------------------------------------------------------------
+// 3 CTAs/SM = 168 registers: almost no spills.  At 4 (128 registers) the 220 B of spill traffic per thread competes
+// with the REDs / gathers / shuffles for the LSU pipe that bounds this kernel (measured 12.8 -> 11.8 ms).
 #ifndef L4D_SCATTER_MIN_CTAS
-#define L4D_SCATTER_MIN_CTAS 4
+#define L4D_SCATTER_MIN_CTAS 3
 #endif
 struct DfeatFromTile {
   const float* base;     // this sample's row in its dfeat tile
@@ -407,15 +409,21 @@ __global__ void __launch_bounds__(NT, 4) k_bwd_flowgrid(const __grid_constant__ 
         const float sc = M.gf.scale[l];
         l4d_pos_fract(sc, x, cx, fx); l4d_pos_fract(sc, y, cy, fy); l4d_pos_fract(sc, z, cz, fz);
         const WarpRuns r = l4d_warp_runs((int)(cx + M.gf.res[l] * (cy + M.gf.res[l] * cz)));
+        float s0[8], s1[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float s0 = l4d_seg_sum(w[c] * d0, r.dist), s1 = l4d_seg_sum(w[c] * d1, r.dist);
-          if (r.tail && gc) {
-            atomicAdd(reinterpret_cast<float2*>(gc + (size_t)idx[c] * 2), make_float2(s0, s1));
-          } else if (r.tail) {
-            float* q = gb + (size_t)idx[c] * 8;
-            l4d_red4(q, b[0] * s0, b[0] * s1, b[1] * s0, b[1] * s1);
-            l4d_red4(q + 4, b[2] * s0, b[2] * s1, b[3] * s0, b[3] * s1);
+        for (int c = 0; c < 8; ++c) { s0[c] = w[c] * d0; s1[c] = w[c] * d1; }
+        l4d_seg_sum8(s0, r);
+        l4d_seg_sum8(s1, r);
+        if (r.tail) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (gc) {
+              atomicAdd(reinterpret_cast<float2*>(gc + (size_t)idx[c] * 2), make_float2(s0[c], s1[c]));
+            } else {
+              float* q = gb + (size_t)idx[c] * 8;
+              l4d_red4(q, b[0] * s0[c], b[0] * s1[c], b[1] * s0[c], b[1] * s1[c]);
+              l4d_red4(q + 4, b[2] * s0[c], b[2] * s1[c], b[3] * s0[c], b[3] * s1[c]);
+            }
           }
         }
       } else if (active && gc) {
