@@ -33,8 +33,14 @@ struct SplitArgs {
 // FLOW_GIVEN: the flow was already written by k_fwd_flow_tc; then this kernel has no MLP at all.
 // TILE: features go out as the fp16 hi|lo operand tiles of the tensor-core dense kernels (SavedView::feat_tc);
 // the sample space is then walked in whole 128-row tiles so the rows past the end of a ray get zeros.
+// Occupancy of the MLP-free variant, measured at L=16 (ms per 8192 rays): 3 CTAs/SM 12.8, 4: 11.2, 5: 10.2, 6: 9.9,
+// 7: 10.6, 8: 10.7 -> 6 (80 registers, 24 B of spills).  The variant that also runs the flow MLP keeps 64
+// accumulators live and stays at 4.
+#ifndef L4D_GATHER_MIN_CTAS
+#define L4D_GATHER_MIN_CTAS 6
+#endif
 template <int NT, bool FLOW_GIVEN, bool TILE>
-__global__ void __launch_bounds__(NT, 4) k_fwd_gather(const __grid_constant__ SplitArgs A) {
+__global__ void __launch_bounds__(NT, FLOW_GIVEN ? L4D_GATHER_MIN_CTAS : 4) k_fwd_gather(const __grid_constant__ SplitArgs A) {
   extern __shared__ __align__(16) float smem[];
   float* xb = smem + threadIdx.x;          // exchange column for the flow MLP, stride NT
   const DevModel& M = A.M;
