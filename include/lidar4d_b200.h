@@ -201,6 +201,20 @@ int    l4d_density_forward(const L4DConfig* cfg, const void* staged, const L4DFr
 int    l4d_attribute_forward(const L4DConfig* cfg, const void* staged, const float* d, const float* geo,
                              const unsigned char* mask_or_null, uint32_t n, float* out, void* stream);
 
+/* --- SURVEY 8(f) "next" row 1: the chamfer / nearest-neighbour op of utils/chamfer3D --------------------------
+ * Replaces chamfer_cuda.cpp:17-32 `forward(xyz1,xyz2,dist1,dist2,idx1,idx2)` / `backward(...)` (kernels
+ * chamfer3D.cu:11-133,154-174).  xyz1[b,n,3], xyz2[b,m,3] fp32 contiguous; dist1[b,n] = squared distance to the
+ * nearest point of xyz2 and idx1[b,n] its index (the smallest index on ties), dist2/idx2 likewise for xyz2.
+ * `work` = l4d_chamfer_work_bytes(b,n,m) scratch bytes.  backward ACCUMULATES into g_xyz1[b,n,3], g_xyz2[b,m,3]
+ * (zero them first, as dist_chamfer_3D.py:66-70 does). */
+size_t l4d_chamfer_work_bytes(uint32_t b, uint32_t n, uint32_t m);
+int    l4d_chamfer_forward(const float* xyz1, const float* xyz2, uint32_t b, uint32_t n, uint32_t m,
+                           float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                           void* work, size_t work_bytes, void* stream);
+int    l4d_chamfer_backward(const float* xyz1, const float* xyz2, uint32_t b, uint32_t n, uint32_t m,
+                            const float* g_dist1, const float* g_dist2, const int32_t* idx1, const int32_t* idx2,
+                            float* g_xyz1, float* g_xyz2, void* stream);
+
 /* --- profiling aid: while started, CUDA events are recorded on the launch stream around every kernel of
  *     l4d_render_forward / l4d_render_backward.  l4d_profile_stop returns the number of (kernel name, ms)
  *     pairs written (static strings), or a negative error code.  Not thread-safe. --------------------------- */

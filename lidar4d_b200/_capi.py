@@ -138,7 +138,7 @@ LIB_NAME = "liblidar4d_b200.so"
 EXPORTS = [
     "l4d_abi_version", "l4d_last_error", "l4d_staged_bytes", "l4d_stage_params", "l4d_saved_bytes",
     "l4d_render_forward", "l4d_grad_work_bytes", "l4d_render_backward", "l4d_unstage_grads",
-    "l4d_flow_forward", "l4d_flow_backward", "l4d_hash_indices", "l4d_density_forward", "l4d_attribute_forward", "l4d_tc_selftest", "l4d_tc_selftest2", "l4d_profile_start", "l4d_profile_stop",
+    "l4d_flow_forward", "l4d_flow_backward", "l4d_hash_indices", "l4d_density_forward", "l4d_attribute_forward", "l4d_chamfer_work_bytes", "l4d_chamfer_forward", "l4d_chamfer_backward", "l4d_tc_selftest", "l4d_tc_selftest2", "l4d_profile_start", "l4d_profile_stop",
 ]
 
 
@@ -174,6 +174,12 @@ def declare(lib, prefix: str = "l4d_", host_sim: bool = False):
         f("density_forward").argtypes = [P(L4DConfig), V, P(L4DFrame), V, U32, V, V, V, V, V]
         lib.l4d_attribute_forward.argtypes = [P(L4DConfig), V, V, V, V, U32, V, V]
         lib.l4d_attribute_forward.restype = C.c_int
+        lib.l4d_chamfer_work_bytes.argtypes = [U32, U32, U32]
+        lib.l4d_chamfer_work_bytes.restype = SZ
+        lib.l4d_chamfer_forward.argtypes = [V, V, U32, U32, U32, V, V, V, V, V, SZ, V]
+        lib.l4d_chamfer_forward.restype = C.c_int
+        lib.l4d_chamfer_backward.argtypes = [V, V, U32, U32, U32, V, V, V, V, V, V, V]
+        lib.l4d_chamfer_backward.restype = C.c_int
         lib.l4d_tc_selftest.argtypes = [V, V, V, U32, U32, V]
         lib.l4d_tc_selftest.restype = C.c_int
         lib.l4d_tc_selftest2.argtypes = [V, V, V, U32, U32, U32, U32, U32, V]

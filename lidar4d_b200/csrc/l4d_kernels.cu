@@ -1231,6 +1231,8 @@ extern "C" int l4d_tc_selftest2(const void* A, const void* B, float* Cout, uint3
   return L4D_OK;
 }
 
+#include "l4d_chamfer.cuh"
+
 #ifdef L4D_PHASE_CLOCKS
 // debug build only: per-phase clock sums of k_bwd_dense_tc (thread 0 of every CTA), cleared on read
 extern "C" int l4d_debug_phase_clocks(unsigned long long* out32) {
