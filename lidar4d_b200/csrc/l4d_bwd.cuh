@@ -268,11 +268,13 @@ struct DfeatFromDh {
   const DevModel* M;
   const BwSample* s;
   L4D_HD float operator()(int row) const { return l4d_dot64(s->dh, M->sig_w1t + (size_t)row * L4D_H); }
+  L4D_HD void ld4(int row, float (&o)[4]) const { for (int i = 0; i < 4; ++i) o[i] = (*this)(row + i); }
 };
 struct DfeatFromPlane {
   const float* base;     // dfeat + p
   size_t stride;         // P
   L4D_HD float operator()(int row) const { return l4d_ld1(base + (size_t)row * stride); }
+  L4D_HD void ld4(int row, float (&o)[4]) const { for (int i = 0; i < 4; ++i) o[i] = (*this)(row + i); }
 };
 
 // scatter dL/dfeature through the encoders of one sample at (x,y,z) with its flow; dflow[6] out
@@ -312,7 +314,7 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
     {   // static planes: product rule over (x,y) (x,z) (y,z)
       float d[8], v0[8], v1[8], v2[8], dummy[8], g[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) d[c] = l4d_dfeat_fn(sc * 8 + c);
+      for (int c = 0; c < 8; c += 4) l4d_dfeat_fn.ld4(sc * 8 + c, *reinterpret_cast<float(*)[4]>(d + c));
       Bilerp b0 = l4d_bilerp(x, R, y, R), b1 = l4d_bilerp(x, R, z, R), b2 = l4d_bilerp(y, R, z, R);
       l4d_plane_sample<false>(M.planes[sc][0], R, b0, v0, dummy);
       l4d_plane_sample<false>(M.planes[sc][1], R, b1, v1, dummy);
@@ -330,7 +332,7 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
     {   // time planes (x,t) (y,t) (z,t): three queries, warped ones also feed d(coords) -> flow
       float d[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) d[c] = l4d_dfeat_fn(row_plane_d + sc * 8 + c);
+      for (int c = 0; c < 8; c += 4) l4d_dfeat_fn.ld4(row_plane_d + sc * 8 + c, *reinterpret_cast<float(*)[4]>(d + c));
 #pragma unroll 1
       for (int qi = 0; qi < 3; ++qi) {
         const float wq = qi == 0 ? wc : (qi == 1 ? wf : wb);
@@ -367,8 +369,9 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
   for (int l = 0; STATIC_HASH && l < L; ++l) {
     uint32_t idx[8]; float w[8];
     l4d_corners3(M.gs, l, x, y, z, idx, w);
-    const float d0 = l4d_dfeat_fn(row_hash_s + 4 * l + 0), d1 = l4d_dfeat_fn(row_hash_s + 4 * l + 1);
-    const float d2 = l4d_dfeat_fn(row_hash_s + 4 * l + 2), d3 = l4d_dfeat_fn(row_hash_s + 4 * l + 3);
+    float dd[4];
+    l4d_dfeat_fn.ld4(row_hash_s + 4 * l, dd);
+    const float d0 = dd[0], d1 = dd[1], d2 = dd[2], d3 = dd[3];
     float* base = G.hs + (size_t)M.gs.offset[l] * 4;
 #pragma unroll
     for (int c = 0; c < 8; ++c) l4d_red4(base + (size_t)idx[c] * 4, w[c] * d0, w[c] * d1, w[c] * d2, w[c] * d3);
@@ -381,11 +384,16 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
     float* glo = G.hd[p][F.cur.slice_lo];
     float* ghi = G.hd[p][F.cur.slice_hi];
     float* gcomb = G.hd_comb[p];
+    float dq[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool quads = (L & 3) == 0;             // rows of a plane start on a multiple of 4: one 16-byte load per 4 levels
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
       uint32_t idx[4]; float w[4];
       l4d_corners2(M.gd[p], l, ca, cb, idx, w);
-      const float d = wc * l4d_dfeat_fn(row_hash_d + p * L + l);
+      if (quads && (l & 3) == 0) l4d_dfeat_fn.ld4(row_hash_d + p * L + l, dq);
+      const int li = l & 3;
+      const float dsel = li == 0 ? dq[0] : (li == 1 ? dq[1] : (li == 2 ? dq[2] : dq[3]));
+      const float d = wc * (quads ? dsel : l4d_dfeat_fn(row_hash_d + p * L + l));
       const float e0 = d * F.cur.basis[0], e1 = d * F.cur.basis[1], e2 = d * F.cur.basis[2], e3 = d * F.cur.basis[3];
       const float slo = F.cur.single ? 1.0f : F.cur.w_lo;
       const size_t off = (size_t)M.gd[p].offset[l] * 4;

@@ -106,6 +106,7 @@ struct SavedView {
   float* flow;      // [6][P]   flow-field output (split pipeline: the scatter kernel needs the warped positions)
   float* dfeat;     // dL/dfeature, dense backward -> scatter kernels: [ray][tile][k/4][128 rows][4] (float4 per row)
   float* dflow;     // [6][P]   dL/dflow, scatter kernel -> flow backward kernel
+  float* tstart;    // [ray][tile] transmittance at the start of every 128-sample tile (tensor-core dense kernels)
   size_t P;
   uint32_t n_tiles;   // 128-sample tiles per ray
   uint32_t x_chunks;  // stored 16-byte chunks per row of a feature tile = ceil(sigma_in_dim / 8)

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(128) k_fwd_dense_tc(const __grid_constant__ Sp
       const uint32_t j = j0 + tid;
       const bool valid = j < S;
       const size_t p = (size_t)ray * S + (valid ? j : 0);
+      if (tid == 0 && A.train) A.sv.tstart[(size_t)ray * n_tiles + (j0 >> 7)] = carry;     // the backward starts every tile from here
       mbar_wait(&s_xbar, xphase);      // this tile's features have landed
       xphase ^= 1u;
       ms.publish();
@@ -557,22 +558,8 @@ __global__ void __launch_bounds__(256) k_bwd_dense_tc(const __grid_constant__ Sp
       s_cdir2[tid] = c - l4d_ld1(M.att_w1t[tid >> 6] + (size_t)M.attr_in_dim * L4D_H + (tid & 63));
     }
     __syncthreads();
-    {   // pass 1: transmittance at the start of every tile
-      float carry = 1.f;
-      for (int t = 0; t < n_tiles; ++t) {
-        const uint32_t j = (uint32_t)t * 128 + row;
-        float v = 1.f;
-        if (j < S) {
-          const float zj = l4d_z(rs, rg, j);
-          const float delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
-          v = (1.0f - l4d_alpha(M, delta, A.sv.sigma[(size_t)ray * S + j])) + 1e-15f;
-        }
-        if (tid == 0) s_tstart[t] = carry;
-        float total;
-        half_excl_prod(v, s_w, total);
-        carry *= total;
-      }
-    }
+    // transmittance at the start of every tile: saved by k_fwd_dense_tc
+    for (int t = tid; t < n_tiles; t += 256) s_tstart[t] = __ldg(A.sv.tstart + (size_t)ray * A.sv.n_tiles + t);
     __syncthreads();
     L4D_PH(0);
     float suffix = 0.f;

@@ -196,7 +196,7 @@ static inline void build_grads(const L4DConfig* c, const L4DMasterGrads* g, void
 
 #define L4D_NT 128
 #define L4D_BWD_SCRATCH_CTAS 1024
-struct SavedLayout { size_t feat, flow_in, sigma, attr, hidden, flow, dfeat, dflow, total; };
+struct SavedLayout { size_t feat, flow_in, sigma, attr, hidden, flow, dfeat, dflow, tstart, total; };
 static inline SavedLayout saved_layout(const L4DConfig* c, uint32_t n_rays, uint32_t S) {
   SavedLayout L;
   const size_t P = (size_t)n_rays * S;
@@ -214,6 +214,7 @@ static inline SavedLayout saved_layout(const L4DConfig* c, uint32_t n_rays, uint
   L.flow = take(P * 6 * sizeof(float));
   L.dfeat = take(tiles * ((c->sigma_in_dim + 3) / 4) * 2048);
   L.dflow = take(P * 6 * sizeof(float));
+  L.tstart = take(tiles * sizeof(float));
   L.total = o;
   return L;
 }
@@ -233,6 +234,7 @@ static inline SavedView saved_view(const L4DConfig* c, void* saved, uint32_t n_r
   v.flow = reinterpret_cast<float*>(b + L.flow);
   v.dfeat = reinterpret_cast<float*>(b + L.dfeat);
   v.dflow = reinterpret_cast<float*>(b + L.dflow);
+  v.tstart = reinterpret_cast<float*>(b + L.tstart);
   v.P = (size_t)n_rays * S;
   return v;
 }

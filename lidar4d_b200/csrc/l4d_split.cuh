@@ -305,6 +305,10 @@ struct DfeatFromTile {
   const float* base;     // this sample's row in its dfeat tile
   bool on;
   __device__ __forceinline__ float operator()(int k) const { return on ? __ldg(base + l4d_dfeat_k(k)) : 0.f; }
+  __device__ __forceinline__ void ld4(int k, float (&o)[4]) const {        // k % 4 == 0: the float4 of the tile row
+    const float4 v = on ? __ldg(reinterpret_cast<const float4*>(base + l4d_dfeat_k(k))) : make_float4(0.f, 0.f, 0.f, 0.f);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
 };
 
 template <int NT>
