@@ -884,6 +884,14 @@ static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid, int
   if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
   if (per_sm < 1) per_sm = 1;
   if (force_per_sm > 0) per_sm = force_per_sm;
+  // small-shared-memory kernels: ask for just the carve-out the resident CTAs need, the rest stays L1 (the driver's
+  // default for k_fwd_gather was 132 KB of shared memory for 55 KB of use, i.e. half of the L1 given away)
+  if (smem <= 16 * 1024) {
+    const size_t need = (size_t)per_sm * (smem + 1024);
+    int pct = (int)((need * 100 + 233471) / 233472);
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
   long g = (long)per_sm * sm_count();
   if ((long)work < g) g = work;
   if (g < 1) g = 1;
