@@ -94,198 +94,6 @@ __host__ __device__ inline DenseFwdSmem dense_fwd_smem(uint32_t in_pad) {
   return L;
 }
 
-// -------------------------------------------------------------------------------------------
-// forward 2/2 on tensor cores: sigma MLP, compositing, attribute heads.  One CTA per ray.
-// TMEM columns: [0,64) sigma hidden / attribute layer-2 net0, [64,128) attribute layer-2 net1,
-//               [128,144) sigma output, [256,384) attribute layer-1 (both heads)
-// -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_fwd_dense_tc(const __grid_constant__ SplitArgs A) {
-  using namespace l4dtc;
-  extern __shared__ __align__(1024) unsigned char dsm[];
-  __shared__ __align__(8) uint64_t s_bar, s_xbar;
-  __shared__ uint32_t s_tmem;
-  const DevModel& M = A.M;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t in_pad = M.sigma_in_pad;
-  const DenseFwdSmem L = dense_fwd_smem(in_pad);
-  unsigned char *xh = dsm + L.xh, *xl = dsm + L.xl, *hh = dsm + L.hh, *hl = dsm + L.hl, *gh = dsm + L.gh, *gl = dsm + L.gl;
-  float* s_enc = reinterpret_cast<float*>(dsm + L.misc);
-  float* s_cdir = s_enc + 80;
-  float* s_w = s_cdir + 128;
-  const uint32_t sb = smem_u32(dsm);
-
-  if (tid == 0) { mbar_init(&s_bar, 1); mbar_init(&s_xbar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(&s_tmem, 512);
-  // weights -> shared memory (already in operand layout in global memory)
-  {
-    auto cp = [&](uint32_t off, const __half* src, uint32_t bytes) {
-      for (uint32_t i = tid * 16; i < bytes; i += 128 * 16)
-        *reinterpret_cast<uint4*>(dsm + off + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(src) + i));
-    };
-    cp(L.w1, M.tc_sig_w1, in_pad * 64 * 2);
-    cp(L.w2, M.tc_sig_w2, 64 * 16 * 2);
-    cp(L.wa1, M.tc_att_w1g, 16 * 128 * 2);
-    cp(L.wa2[0], M.tc_att_w2[0], 64 * 64 * 2);
-    cp(L.wa2[1], M.tc_att_w2[1], 64 * 64 * 2);
-  }
-  MmaSync ms{&s_bar, 0u};
-  ms.publish();
-  const uint32_t tm = s_tmem;
-  const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16);
-  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
-  const uint32_t S = A.S;
-  const int n_xchunks = (int)in_pad / 8;
-  // feature tiles arrive as fp16 hi|lo operand tiles (written by k_fwd_gather) with one bulk copy per half; the copy of
-  // the next tile is issued as soon as the last MMA that reads the X buffer has completed
-  const uint32_t xbytes = A.sv.x_chunks * 2048u;
-  const uint32_t n_tiles = A.sv.n_tiles;
-  uint32_t xphase = 0u;
-  auto x_issue = [&](uint32_t r, uint32_t t) {
-    // tcnn's ones-padding chunks are not stored in global memory
-    for (int c = (int)A.sv.x_chunks; c < n_xchunks; ++c) {
-      *reinterpret_cast<uint4*>(tile_chunk(xh, tid, c)) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
-      *reinterpret_cast<uint4*>(tile_chunk(xl, tid, c)) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    if (tid == 0) {
-      const unsigned char* src = A.sv.feat_tc + ((size_t)r * n_tiles + t) * (size_t)(2u * xbytes);
-      mbar_expect_tx(&s_xbar, 2u * xbytes);
-      bulk_g2s(sb + L.xh, src, xbytes, &s_xbar);
-      bulk_g2s(sb + L.xl, src + xbytes, xbytes, &s_xbar);
-    }
-  };
-  auto x_issue_next = [&](uint32_t r, uint32_t t) {
-    if (t + 1 < n_tiles) x_issue(r, t + 1);
-    else if (r + gridDim.x < A.n_rays) x_issue(r + gridDim.x, 0u);
-  };
-  if (blockIdx.x < A.n_rays) x_issue(blockIdx.x, 0u);
-
-  for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
-    const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
-    __syncthreads();
-    for (int i = tid; i < L4D_ENC; i += 128) {
-      const int dim = i / 24, k = (i % 24) >> 1, ph = i & 1;
-      s_enc[i] = l4d_freq(dim == 0 ? dx : (dim == 1 ? dy : dz), k, ph);
-    }
-    __syncthreads();
-    s_cdir[tid] = l4d_attr_cdir(M, tid >> 6, tid & 63, s_enc);
-    __syncthreads();
-    float carry = 1.f, pd = 0.f, p0 = 0.f, p1 = 0.f, pw = 0.f;
-    const uint64_t rg = A.ray_offset + ray;
-    for (uint32_t j0 = 0; j0 < S; j0 += 128) {
-      const uint32_t j = j0 + tid;
-      const bool valid = j < S;
-      const size_t p = (size_t)ray * S + (valid ? j : 0);
-      if (tid == 0 && A.train) A.sv.tstart[(size_t)ray * n_tiles + (j0 >> 7)] = carry;     // the backward starts every tile from here
-      mbar_wait(&s_xbar, xphase);      // this tile's features have landed
-      xphase ^= 1u;
-      ms.publish();
-      if (tid == 0) {
-        mma_chunks(tm + 0, sb + L.xh, sb + L.w1, 64, n_xchunks, false);
-        mma_chunks(tm + 0, sb + L.xl, sb + L.w1, 64, n_xchunks, true);
-        ms.commit();
-      }
-      ms.wait();
-      // ---- hidden = relu(.) -> hi/lo tile ----
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[16];
-        tmem_ld16(tlane + (uint32_t)(q * 16), v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        tile_put8(hh, hl, tid, 2 * q, v);
-        tile_put8(hh, hl, tid, 2 * q + 1, v + 8);
-      }
-      ms.publish();
-      if (tid == 0) {
-        mma_chunks(tm + 128, sb + L.hh, sb + L.w2, 16, 8, false);
-        mma_chunks(tm + 128, sb + L.hl, sb + L.w2, 16, 8, true);
-        ms.commit();
-      }
-      ms.wait();
-      float out[16];
-      tmem_ld16(tlane + 128u, out);
-      float zj = 0.f, alpha = 0.f, sigma = 0.f;
-      if (valid) {
-        sigma = expf(out[0]);
-        zj = l4d_z(rs, rg, j);
-        const float delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
-        alpha = l4d_alpha(M, delta, sigma);
-      }
-      const float vv = valid ? (1.0f - alpha) + 1e-15f : 1.f;
-      float total;
-      const float T = carry * block_excl_prod<128>(vv, s_w, total);
-      carry *= total;
-      const float w = alpha * T;
-      const bool masked = valid && w > 1e-4f;
-      float a0 = 0.f, a1 = 0.f;
-      const bool any_masked = __syncthreads_or(masked ? 1 : 0) != 0;
-      if (!any_masked) x_issue_next(ray, j0 >> 7);       // the X buffer is free already
-      if (any_masked) {
-        // ---- attribute heads: [geo,0] (K=16) -> 2x64 -> relu -> 64 -> relu -> dot w3 -> sigmoid ----
-        float g[16];
-#pragma unroll
-        for (int i = 0; i < 15; ++i) g[i] = masked ? out[1 + i] : 0.f;
-        g[15] = 0.f;
-        tile_put8(gh, gl, tid, 0, g);
-        tile_put8(gh, gl, tid, 1, g + 8);
-        ms.publish();
-        if (tid == 0) {
-          mma_chunks(tm + 256, sb + L.gh, sb + L.wa1, 128, 2, false);
-          mma_chunks(tm + 256, sb + L.gl, sb + L.wa1, 128, 2, true);
-          ms.commit();
-        }
-        ms.wait();
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {       // 128 columns: net0 hidden | net1 hidden -> chunks 0..15 of the x tile
-          float v[16];
-          tmem_ld16(tlane + 256u + (uint32_t)(q * 16), v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + s_cdir[q * 16 + i], 0.f);
-          tile_put8(xh, xl, tid, 2 * q, v);
-          tile_put8(xh, xl, tid, 2 * q + 1, v + 8);
-        }
-        ms.publish();
-        if (tid == 0) {
-#pragma unroll
-          for (int net = 0; net < 2; ++net) {
-            mma_chunks(tm + (uint32_t)(net * 64), sb + L.xh + (uint32_t)net * 8u * 2048u, sb + L.wa2[net], 64, 8, false);
-            mma_chunks(tm + (uint32_t)(net * 64), sb + L.xl + (uint32_t)net * 8u * 2048u, sb + L.wa2[net], 64, 8, true);
-          }
-          ms.commit();
-        }
-        ms.wait();
-        x_issue_next(ray, j0 >> 7);                    // the attribute hidden tile (in the X buffer) has been consumed
-        float o[2] = {0.f, 0.f};
-#pragma unroll
-        for (int net = 0; net < 2; ++net) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[16];
-            tmem_ld16(tlane + (uint32_t)(net * 64 + q * 16), v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[net] = fmaf(fmaxf(v[i], 0.f), l4d_ld1(M.att_w3[net] + q * 16 + i), o[net]);
-          }
-        }
-        if (masked) { a0 = l4d_sigmoid(o[0]); a1 = l4d_sigmoid(o[1]); }
-      }
-      pd = fmaf(w, zj, pd); p0 = fmaf(w, a0, p0); p1 = fmaf(w, a1, p1); pw += w;
-      if (valid) {
-        if (A.train) { A.sv.sigma[p] = sigma; A.sv.attr[p] = a0; A.sv.attr[A.sv.P + p] = a1; }
-        if (A.weights) A.weights[p] = w;
-        if (A.zvals) A.zvals[p] = zj;
-      }
-      tc_fence_before();
-      __syncthreads();          // TMEM columns and tiles are reused by the next tile
-      tc_fence_after();
-    }
-    pd = block_sum<128>(pd, s_w); p0 = block_sum<128>(p0, s_w); p1 = block_sum<128>(p1, s_w); pw = block_sum<128>(pw, s_w);
-    if (tid == 0) { A.depth[ray] = pd; A.image[2 * ray] = p0; A.image[2 * ray + 1] = p1; A.wsum[ray] = pw; }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 512);
-}
-
 // =============================================================================================
 // backward 1/3 on tensor cores.
 //
@@ -425,6 +233,225 @@ __device__ __forceinline__ float block_amax256(float v, float* s_w) {
   return r;
 }
 }  // namespace l4dtc
+
+// -------------------------------------------------------------------------------------------
+// forward 2/2 on tensor cores: sigma MLP, compositing, attribute heads.  One CTA per ray, 256 threads: two threads per
+// row (sample) split the columns of every epilogue; in the attribute phase thread half h owns head h.
+// TMEM columns: [0,64) sigma hidden / attribute layer-2 net0, [64,128) attribute layer-2 net1,
+//               [128,144) sigma output, [256,384) attribute layer-1 (both heads)
+// -------------------------------------------------------------------------------------------
+namespace l4dtc {
+// sum over the 128 rows of one thread half (warps 0-3 / 4-7) of a 256-thread CTA; every thread of the half gets it
+__device__ __forceinline__ float half_sum(float v, float* s_w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, base = warp & 4;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) s_w[warp] = v;
+  __syncthreads();
+  const float r = (s_w[base] + s_w[base + 1]) + (s_w[base + 2] + s_w[base + 3]);
+  __syncthreads();
+  return r;
+}
+}  // namespace l4dtc
+
+__global__ void __launch_bounds__(256) k_fwd_dense_tc(const __grid_constant__ SplitArgs A) {
+  using namespace l4dtc;
+  extern __shared__ __align__(1024) unsigned char dsm[];
+  __shared__ __align__(8) uint64_t s_bar, s_xbar;
+  __shared__ uint32_t s_tmem;
+  const DevModel& M = A.M;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7, wq = warp & 3;
+  const uint32_t in_pad = M.sigma_in_pad;
+  const DenseFwdSmem L = dense_fwd_smem(in_pad);
+  unsigned char *xh = dsm + L.xh, *xl = dsm + L.xl, *hh = dsm + L.hh, *hl = dsm + L.hl, *gh = dsm + L.gh, *gl = dsm + L.gl;
+  float* s_enc = reinterpret_cast<float*>(dsm + L.misc);
+  float* s_cdir = s_enc + 80;
+  float* s_w = s_cdir + 128;
+  const uint32_t sb = smem_u32(dsm);
+
+  if (tid == 0) { mbar_init(&s_bar, 1); mbar_init(&s_xbar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&s_tmem, 512);
+  // weights -> shared memory (already in operand layout in global memory)
+  {
+    auto cp = [&](uint32_t off, const __half* src, uint32_t bytes) {
+      for (uint32_t i = tid * 16; i < bytes; i += 256 * 16)
+        *reinterpret_cast<uint4*>(dsm + off + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(src) + i));
+    };
+    cp(L.w1, M.tc_sig_w1, in_pad * 64 * 2);
+    cp(L.w2, M.tc_sig_w2, 64 * 16 * 2);
+    cp(L.wa1, M.tc_att_w1g, 16 * 128 * 2);
+    cp(L.wa2[0], M.tc_att_w2[0], 64 * 64 * 2);
+    cp(L.wa2[1], M.tc_att_w2[1], 64 * 64 * 2);
+  }
+  MmaSync ms{&s_bar, 0u};
+  ms.publish();
+  const uint32_t tm = s_tmem;
+  const uint32_t tlane = tm + ((uint32_t)(wq * 32) << 16);
+  const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
+  const uint32_t S = A.S;
+  const int n_xchunks = (int)in_pad / 8;
+  // feature tiles arrive as fp16 hi|lo operand tiles (written by k_fwd_gather) with one bulk copy per half; the copy of
+  // the next tile is issued as soon as the last MMA that reads the X buffer has completed
+  const uint32_t xbytes = A.sv.x_chunks * 2048u;
+  const uint32_t n_tiles = A.sv.n_tiles;
+  uint32_t xphase = 0u;
+  auto x_issue = [&](uint32_t r, uint32_t t) {
+    if (half == 0) {       // tcnn's ones-padding chunks are not stored in global memory
+      for (int c = (int)A.sv.x_chunks; c < n_xchunks; ++c) {
+        *reinterpret_cast<uint4*>(tile_chunk(xh, row, c)) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+        *reinterpret_cast<uint4*>(tile_chunk(xl, row, c)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    if (tid == 0) {
+      const unsigned char* src = A.sv.feat_tc + ((size_t)r * n_tiles + t) * (size_t)(2u * xbytes);
+      mbar_expect_tx(&s_xbar, 2u * xbytes);
+      bulk_g2s(sb + L.xh, src, xbytes, &s_xbar);
+      bulk_g2s(sb + L.xl, src + xbytes, xbytes, &s_xbar);
+    }
+  };
+  auto x_issue_next = [&](uint32_t r, uint32_t t) {
+    if (t + 1 < n_tiles) x_issue(r, t + 1);
+    else if (r + gridDim.x < A.n_rays) x_issue(r + gridDim.x, 0u);
+  };
+  if (blockIdx.x < A.n_rays) x_issue(blockIdx.x, 0u);
+
+  for (uint32_t ray = blockIdx.x; ray < A.n_rays; ray += gridDim.x) {
+    const float dx = __ldg(A.rays_d + 3 * ray), dy = __ldg(A.rays_d + 3 * ray + 1), dz = __ldg(A.rays_d + 3 * ray + 2);
+    __syncthreads();
+    for (int i = tid; i < L4D_ENC; i += 256) {
+      const int dim = i / 24, k = (i % 24) >> 1, ph = i & 1;
+      s_enc[i] = l4d_freq(dim == 0 ? dx : (dim == 1 ? dy : dz), k, ph);
+    }
+    __syncthreads();
+    if (tid < 128) s_cdir[tid] = l4d_attr_cdir(M, tid >> 6, tid & 63, s_enc);
+    __syncthreads();
+    // per-thread partial sums over this thread's row: half 0 carries depth, weight sum and head 0, half 1 carries head 1
+    float carry = 1.f, pd = 0.f, pa = 0.f, pw = 0.f;
+    const uint64_t rg = A.ray_offset + ray;
+    for (uint32_t j0 = 0; j0 < S; j0 += 128) {
+      const uint32_t j = j0 + row;
+      const bool valid = j < S;
+      const size_t p = (size_t)ray * S + (valid ? j : 0);
+      if (tid == 0 && A.train) A.sv.tstart[(size_t)ray * n_tiles + (j0 >> 7)] = carry;     // the backward starts every tile from here
+      mbar_wait(&s_xbar, xphase);      // this tile's features have landed
+      xphase ^= 1u;
+      ms.publish();
+      if (tid == 0) {
+        mma_chunks(tm + 0, sb + L.xh, sb + L.w1, 64, n_xchunks, false);
+        mma_chunks(tm + 0, sb + L.xl, sb + L.w1, 64, n_xchunks, true);
+        ms.commit();
+      }
+      ms.wait();
+      // ---- hidden = relu(.) -> hi/lo tile (each half its 32 columns) ----
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+        const int q = 2 * half + qq;
+        float v[16];
+        tmem_ld16(tlane + (uint32_t)(q * 16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        tile_put8(hh, hl, row, 2 * q, v);
+        tile_put8(hh, hl, row, 2 * q + 1, v + 8);
+      }
+      ms.publish();
+      if (tid == 0) {
+        mma_chunks(tm + 128, sb + L.hh, sb + L.w2, 16, 8, false);
+        mma_chunks(tm + 128, sb + L.hl, sb + L.w2, 16, 8, true);
+        ms.commit();
+      }
+      ms.wait();
+      float out[16];
+      tmem_ld16(tlane + 128u, out);
+      float zj = 0.f, alpha = 0.f, sigma = 0.f;
+      if (valid) {
+        sigma = expf(out[0]);
+        zj = l4d_z(rs, rg, j);
+        const float delta = (j + 1 < S) ? (l4d_z(rs, rg, j + 1) - zj) : rs.sample_dist;
+        alpha = l4d_alpha(M, delta, sigma);
+      }
+      const float vv = valid ? (1.0f - alpha) + 1e-15f : 1.f;
+      float total;
+      const float T = carry * half_excl_prod(vv, s_w, total);      // both halves run the same 128-row scan
+      carry *= total;
+      const float w = alpha * T;
+      const bool masked = valid && w > 1e-4f;
+      float a = 0.f;                     // this half's attribute head
+      const bool any_masked = __syncthreads_or(masked ? 1 : 0) != 0;
+      if (!any_masked) x_issue_next(ray, j0 >> 7);       // the X buffer is free already
+      if (any_masked) {
+        // ---- attribute heads: [geo,0] (K=16) -> 2x64 -> relu -> 64 -> relu -> dot w3 -> sigmoid ----
+        {
+          float g8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float gv = half ? (i < 7 ? out[9 + i] : 0.f) : out[1 + i];      // geo[0..7] | geo[8..14], 0
+            g8[i] = masked ? gv : 0.f;
+          }
+          tile_put8(gh, gl, row, half, g8);
+        }
+        ms.publish();
+        if (tid == 0) {
+          mma_chunks(tm + 256, sb + L.gh, sb + L.wa1, 128, 2, false);
+          mma_chunks(tm + 256, sb + L.gl, sb + L.wa1, 128, 2, true);
+          ms.commit();
+        }
+        ms.wait();
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {     // 128 columns: net0 hidden | net1 hidden -> chunks 0..15 of the x tile
+          const int q = 4 * half + qq;
+          float v[16];
+          tmem_ld16(tlane + 256u + (uint32_t)(q * 16), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + s_cdir[q * 16 + i], 0.f);
+          tile_put8(xh, xl, row, 2 * q, v);
+          tile_put8(xh, xl, row, 2 * q + 1, v + 8);
+        }
+        ms.publish();
+        if (tid == 0) {
+#pragma unroll
+          for (int net = 0; net < 2; ++net) {
+            mma_chunks(tm + (uint32_t)(net * 64), sb + L.xh + (uint32_t)net * 8u * 2048u, sb + L.wa2[net], 64, 8, false);
+            mma_chunks(tm + (uint32_t)(net * 64), sb + L.xl + (uint32_t)net * 8u * 2048u, sb + L.wa2[net], 64, 8, true);
+          }
+          ms.commit();
+        }
+        ms.wait();
+        x_issue_next(ray, j0 >> 7);                    // the attribute hidden tile (in the X buffer) has been consumed
+        float o = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[16];
+          tmem_ld16(tlane + (uint32_t)(half * 64 + q * 16), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o = fmaf(fmaxf(v[i], 0.f), l4d_ld1(M.att_w3[half] + q * 16 + i), o);
+        }
+        if (masked) a = l4d_sigmoid(o);
+      }
+      pa = fmaf(w, a, pa);
+      if (half == 0) { pd = fmaf(w, zj, pd); pw += w; }
+      if (valid) {
+        if (A.train) {
+          if (half == 0) A.sv.sigma[p] = sigma;
+          A.sv.attr[(size_t)half * A.sv.P + p] = a;
+        }
+        if (half == 0) {
+          if (A.weights) A.weights[p] = w;
+          if (A.zvals) A.zvals[p] = zj;
+        }
+      }
+      tc_fence_before();
+      __syncthreads();          // TMEM columns and tiles are reused by the next tile
+      tc_fence_after();
+    }
+    pd = half_sum(pd, s_w); pa = half_sum(pa, s_w); pw = half_sum(pw, s_w);
+    if (tid == 0) { A.depth[ray] = pd; A.image[2 * ray] = pa; A.wsum[ray] = pw; }
+    if (tid == 128) A.image[2 * ray + 1] = pa;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
 
 #ifdef L4D_PHASE_CLOCKS
 __device__ unsigned long long g_phase_clk[32];

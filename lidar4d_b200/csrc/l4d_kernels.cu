@@ -986,9 +986,9 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
   if (use_tc_dense(cfg)) {
     const size_t smem = dense_fwd_smem(cfg->sigma_in_pad).total + 1024;
     int grid;
-    rc = grid_for(k_fwd_dense_tc, 128, smem, rays->n_rays, grid);
+    rc = grid_for(k_fwd_dense_tc, 256, smem, rays->n_rays, grid);
     if (rc != L4D_OK) return rc;
-    k_fwd_dense_tc<<<grid, 128, smem, st>>>(A);
+    k_fwd_dense_tc<<<grid, 256, smem, st>>>(A);
     prof_mark(st, "k_fwd_dense_tc");
   } else {
     const size_t smem = (64 * L4D_NT + 80 + 128 + 32) * sizeof(float);
