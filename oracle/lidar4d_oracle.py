@@ -391,13 +391,13 @@ class OracleLiDAR4D(nn.Module):
             x1 = x01 + flow[:, :3]
             with torch.no_grad():
                 hash_1 = self.hash_dynamic(x1, fr.fwd)
-            xt1 = torch.cat([x1, torch.full((N, 1), float(fr.fwd.tau), dtype=x01.dtype)], -1)
+            xt1 = torch.cat([x1, torch.full((N, 1), float(fr.fwd.tau), dtype=x01.dtype, device=x01.device)], -1)
             plane_1 = self.planes(xt1, "dynamic")
         if fr.has_bwd:
             x2 = x01 + flow[:, 3:]
             with torch.no_grad():
                 hash_2 = self.hash_dynamic(x2, fr.bwd)
-            xt2 = torch.cat([x2, torch.full((N, 1), float(fr.bwd.tau), dtype=x01.dtype)], -1)
+            xt2 = torch.cat([x2, torch.full((N, 1), float(fr.bwd.tau), dtype=x01.dtype, device=x01.device)], -1)
             plane_2 = self.planes(xt2, "dynamic")
         plane_d = 0.5 * plane_d + 0.25 * (plane_1 + plane_2)
         hash_d = 0.5 * hash_d + 0.25 * (hash_1 + hash_2)
@@ -414,7 +414,7 @@ class OracleLiDAR4D(nn.Module):
         """lidar4d.py:191-223 (x is unused by the reference's attribute heads)."""
         c = self.cfg
         N = d.shape[0]
-        out = torch.zeros(N, c.out_lidar_dim, dtype=self.cd)
+        out = torch.zeros(N, c.out_lidar_dim, dtype=self.cd, device=d.device)
         if mask is not None:
             if not bool(mask.any()):
                 return out
@@ -442,11 +442,11 @@ class OracleLiDAR4D(nn.Module):
         near, far = np.float32(c.near_lidar), np.float32(c.far_lidar)
         lin = sample_lin(num_steps) if lin is None else lin
         z1 = (near + (far - near) * lin).astype(np.float32)                     # renderer.py:79
-        z = torch.from_numpy(np.broadcast_to(z1, (N, num_steps)).copy())
+        z = torch.from_numpy(np.broadcast_to(z1, (N, num_steps)).copy()).to(rays_o.device)
         sample_dist = np.float32((far - near) / np.float32(num_steps))          # :82
         if perturb:
             u = jitter_uniform(seed, np.arange(N) + ray_offset, num_steps)
-            z = z + (torch.from_numpy(u) - 0.5) * float(sample_dist)           # :84
+            z = z + (torch.from_numpy(u).to(rays_o.device) - 0.5) * float(sample_dist)           # :84
         xyz = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z.unsqueeze(-1)     # :88
         xyz = torch.min(torch.max(xyz, self.aabb[:3]), self.aabb[3:])           # :89
         dens = self.density(xyz.reshape(-1, 3), fr, return_features=return_stages)

@@ -1,7 +1,7 @@
 """Chamfer op timing on the GPU (CUDA events) next to the CPU oracle on a bounded sample; one JSON line."""
 import json, os, sys, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from lidar4d_b200.chamfer import chamfer_3DDist
 
 dev = torch.device("cuda:0")
