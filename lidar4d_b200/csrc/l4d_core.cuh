@@ -93,8 +93,8 @@ struct DevGrads {
   float *flo_w0t, *flo_w1t, *flo_w2;           // [16][64], [64][64], [8][64]
 };
 
-// where the training-mode forward saves what the backward needs: SoA planes of
-// P = n_rays*n_steps floats each -> every warp store / load is one 128 B line
+// where the training-mode forward saves what the backward needs, and what the kernels of the split pipeline hand
+// to each other.  SoA planes hold P = n_rays*n_steps floats each -> every warp store / load is one 128 B line
 struct SavedView {
   float* feat;      // [sigma_in_dim][P]   (fp32-FMA dense kernels)
   unsigned char* feat_tc;   // same region in the tensor-core path: per 128-sample tile of a ray, the fp16 operand tile

@@ -5,11 +5,14 @@
 // shows both kernels latency-bound on long_scoreboard with DRAM at 2% (profiles/r01_v1_*).  Here
 // the memory-irregular work runs in lean, high-occupancy kernels (thread == sample, grid-stride,
 // no shared memory) and the dense work (MLPs, compositing) in per-ray kernels; they exchange
-// ~1 KB/sample through SoA planes [k][P] (every warp access = one 128 B line), which the idle HBM
-// absorbs.  Same per-sample functions (l4d_core.cuh / l4d_bwd.cuh), same numerics.
+// ~1.6 KB/sample through the buffers of SavedView (l4d_core.cuh): features as the tensor-core operand tiles
+// themselves, dL/dfeature as float4 tiles, the rest as SoA planes [k][P] (every warp access = one 128 B line),
+// which the otherwise idle HBM absorbs.  Same per-sample functions (l4d_core.cuh / l4d_bwd.cuh), same numerics.
 //
-//   forward :  k_fwd_gather  ->  k_fwd_dense
-//   backward:  k_bwd_dense   ->  k_bwd_scatter  ->  k_bwd_flow
+//   forward :  [k_fwd_flow_tc ->] k_fwd_gather -> k_fwd_dense{,_tc}
+//   backward:  k_bwd_dense{,_tc} -> k_bwd_scatter + k_bwd_scatter_static -> k_fold_dynamic
+//              -> k_bwd_flow  |  k_bwd_flow_tc -> k_bwd_flowgrid -> k_fold_flow
+// (the *_tc kernels live in l4d_dense_tc.cuh; DESIGN.md 4.2 has the measured time and limiter of each)
 #pragma once
 #include "l4d_bwd.cuh"
 #include "l4d_core.cuh"

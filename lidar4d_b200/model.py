@@ -112,8 +112,10 @@ class _Engine:
     def __init__(self, owner: "LiDAR4D"):
         self.owner = owner
         self.cfg = owner.cfg
-        self.mlp_fp16 = False
-        self.ccfg = _capi.make_config(self.cfg, False)
+        # default = what the reference does: tiny-cuda-nn's FullyFusedMLP consumes fp16 copies of its fp32 parameters;
+        # this is also the mode that runs the dense kernels on the tcgen05 tensor cores
+        self.mlp_fp16 = True
+        self.ccfg = _capi.make_config(self.cfg, True)
         self.names = _capi.param_names(self.cfg)
         self.lib = None
         self.staged = None
@@ -421,7 +423,8 @@ class LiDAR4D(LiDAR_Renderer):
     def set_mlp_fp16(self, on: bool = True):
         """True: MLP weights are consumed as fp16-rounded working copies of the fp32 masters (exactly how
         tiny-cuda-nn's FullyFusedMLP holds them) and the dense kernels of the split pipeline run on the
-        tcgen05 tensor cores with hi/lo-split fp16 activations (fp32-class accuracy).  False: fp32 weights, FMA."""
+        tcgen05 tensor cores with hi/lo-split fp16 activations (fp32-class accuracy) -- the default.
+        False: fp32 weights on the fp32-FMA kernels (bit-for-bit the fp32 oracle's arithmetic, ~2x slower)."""
         self._engine.set_mlp_fp16(on)
         return self
 

@@ -50,6 +50,8 @@ def cuda_model_from_oracle(oracle, device="cuda"):
                 flow_log2_hashmap_size=c.flow_log2_hashmap_size)
     res = m.load_state_dict(oracle.ref_state_dict(), strict=False)
     assert not res.missing_keys and not res.unexpected_keys, res
+    # same weight precision as the oracle instance: fp32 weights unless the oracle emulates tcnn's fp16 copies
+    m.set_mlp_fp16(getattr(oracle, "mlp_dtype", "fp32") == "fp16")
     return m.to(device)
 
 
