@@ -147,10 +147,11 @@ __global__ void k_chamfer_grad(uint32_t nq, const float* __restrict__ q, uint32_
   atomicAdd(gt + 3 * tj + 2, -(g * (z1 - z2)));
 }
 
-// target splits so that about two waves of CTAs exist even for small query clouds
+// target splits so that every SM gets about eight CTAs (four are resident at a time): with only two per SM the last,
+// partial wave cost 12 % (ncu: 392 CTAs on 148 SMs, 28 % warps active)
 static uint32_t splits_for(uint32_t b, uint32_t nq, uint32_t nt) {
   const uint32_t qblocks = (nq + CH_NT * CH_Q - 1) / (CH_NT * CH_Q);
-  const uint32_t want = 2u * (uint32_t)sm_count();
+  const uint32_t want = 8u * (uint32_t)sm_count();
   uint32_t s = (want + qblocks * b - 1) / (qblocks * b);
   const uint32_t max_s = (nt + 255) / 256;        // at least 256 targets per split
   if (s > max_s) s = max_s;
