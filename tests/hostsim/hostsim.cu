@@ -194,7 +194,11 @@ extern "C" int hs_render_backward(const L4DConfig* cfg, const void* staged, cons
   DevModel M;
   build_model(cfg, staged, M);
   DevGrads G;
-  build_grads(cfg, grads, grad_work, G);
+  // rays->reserved bit 1 (host-sim only): use the slice-independent dynamic-hash accumulators of the split pipeline
+  // (DevGrads::hd_comb) and fold them afterwards exactly like k_fold_dynamic does
+  const bool comb = (rays->reserved & 2u) != 0;
+  build_grads(cfg, grads, grad_work, G, comb);
+  if (comb) G.hf_comb = nullptr;          // the flow-grid accumulator belongs to k_bwd_flowgrid (no host mirror)
   const L4DFrame& F = *frame;
   const uint32_t S = rays->n_steps;
   const int NT = L4D_NT;
@@ -287,6 +291,22 @@ extern "C" int hs_render_backward(const L4DConfig* cfg, const void* staged, cons
           if (r < L4D_ENC) G.att_w1t[net][(size_t)r * 64 + j] += enc[r] * cs;
           else G.att_w1t[net][(size_t)(M.attr_in_dim + (r - L4D_ENC)) * 64 + j] += cs;
         }
+  }
+  if (comb) {          // mirror of k_fold_dynamic (l4d_kernels.cu)
+    const bool single = F.cur.single != 0;
+    const float w_lo = single ? 1.0f : F.cur.w_lo, w_hi = F.cur.w_hi;
+    for (int p = 0; p < 3; ++p) {
+      const size_t n = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels] * 4;
+      float* c = G.hd_comb[p];
+      float* glo = G.hd[p][F.cur.slice_lo];
+      float* ghi = single ? nullptr : G.hd[p][F.cur.slice_hi];
+      for (size_t i = 0; i < n; ++i) {
+        if (c[i] == 0.f) continue;
+        glo[i] = fmaf(w_lo, c[i], glo[i]);
+        if (ghi) ghi[i] = fmaf(w_hi, c[i], ghi[i]);
+        c[i] = 0.f;
+      }
+    }
   }
   return L4D_OK;
 }

@@ -88,7 +88,9 @@ class HostSim:
         work = torch.zeros(self.L.hs_grad_work_bytes(C.byref(self.ccfg)), dtype=torch.uint8)
         return grads, tab, work
 
-    def backward(self, g_depth, g_image, g_wsum=None, g_weights=None):
+    def backward(self, g_depth, g_image, g_wsum=None, g_weights=None, comb=False):
+        """comb=True: dynamic-hash gradients go through the slice-independent accumulators + fold of the split pipeline"""
+        self._rays_s.reserved = 2 if comb else 0
         grads, tab, work = self._grad_tables()
         gd = torch.as_tensor(g_depth, dtype=torch.float32).contiguous()
         gi = torch.as_tensor(g_image, dtype=torch.float32).contiguous()
