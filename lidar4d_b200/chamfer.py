@@ -7,7 +7,6 @@ autograd contract (``chamfer_3DFunction``, dist_chamfer_3D.py:31-73), backed by 
 the kernels run on torch's *current* stream (the reference launches on the default stream,
 chamfer3D.cu:141-142) and return codes are checked (dist_chamfer_3D.py:54 ignores them).
 """
-import ctypes as C
 
 import torch
 from torch import nn

@@ -3,7 +3,7 @@
 The true reference (PyTorch + tiny-cuda-nn) cannot run in this environment; its closest stand-in on a GPU is the
 oracle (the reference's op graph restated in plain torch on the tcnn spec) executed eagerly on the same B200.
 Test infrastructure (lives under tests/, imports oracle/); prints one JSON line."""
-import json, os, sys, time
+import json, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
