@@ -127,24 +127,24 @@ __global__ void k_chamfer_unpack(const unsigned long long* __restrict__ keys, si
   idx[i] = (int)(uint32_t)k;
 }
 
-// chamfer3D.cu:154-174: both ends of every (query, nearest target) pair
+// backward of one direction (semantics of chamfer3D.cu:154-174): with v = 2 * dL/ddist[j] * (q_j - t_nn(j)),
+// the query point receives +v and its nearest target -v.  One thread per query; the query's own gradient row is
+// touched by this thread only in this launch but shared with the other direction's launch, hence atomics on both.
 __global__ void k_chamfer_grad(uint32_t nq, const float* __restrict__ q, uint32_t nt, const float* __restrict__ t, const float* __restrict__ gdist,
                                const int* __restrict__ idx, float* __restrict__ gq, float* __restrict__ gt) {
-  const uint32_t b = blockIdx.y;
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nq) return;
-  const size_t qj = (size_t)b * nq + j;
-  const int j2 = idx[qj];
-  const size_t tj = (size_t)b * nt + (size_t)j2;
-  const float x1 = q[3 * qj], y1 = q[3 * qj + 1], z1 = q[3 * qj + 2];
-  const float x2 = t[3 * tj], y2 = t[3 * tj + 1], z2 = t[3 * tj + 2];
-  const float g = gdist[qj] * 2;
-  atomicAdd(gq + 3 * qj + 0, g * (x1 - x2));
-  atomicAdd(gq + 3 * qj + 1, g * (y1 - y2));
-  atomicAdd(gq + 3 * qj + 2, g * (z1 - z2));
-  atomicAdd(gt + 3 * tj + 0, -(g * (x1 - x2)));
-  atomicAdd(gt + 3 * tj + 1, -(g * (y1 - y2)));
-  atomicAdd(gt + 3 * tj + 2, -(g * (z1 - z2)));
+  const size_t qrow = (size_t)blockIdx.y * nq + j;
+  const size_t trow = (size_t)blockIdx.y * nt + (size_t)idx[qrow];
+  const float scale = gdist[qrow] * 2;
+  float v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] = scale * (q[3 * qrow + c] - t[3 * trow + c]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    atomicAdd(gq + 3 * qrow + c, v[c]);
+    atomicAdd(gt + 3 * trow + c, -v[c]);
+  }
 }
 
 // target splits so that every SM gets about eight CTAs (four are resident at a time): with only two per SM the last,
