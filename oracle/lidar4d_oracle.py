@@ -487,6 +487,41 @@ def randomize_parameters(model: OracleLiDAR4D, seed: int = 0, hash_range: float 
                 v.copy_(torch.randn(v.shape, generator=g) * flow_last_std)
 
 
+MLP_PARAM_NAMES = ("sigma_net/params", "intensity_net/params", "raydrop_net/params",
+                   "flow_net/mlp/0/weight", "flow_net/mlp/2/weight", "flow_net/mlp/4/weight")
+
+
+def snap_mlp_weights_fp16(model: OracleLiDAR4D) -> OracleLiDAR4D:
+    """Round every MLP master weight to an fp16-representable value.  With such masters the fp32-weight function
+    (the reference's python modules on the shim) and the fp16-working-copy function (tiny-cuda-nn's FullyFusedMLP,
+    the tensor-core kernels) are the same function, so one fixture pins both."""
+    with torch.no_grad():
+        for k in MLP_PARAM_NAMES:
+            v = model.P[k]
+            v.copy_(v.to(torch.float16).to(v.dtype))
+    return model
+
+
+def projection_vector(n: int) -> np.ndarray:
+    """Deterministic float64 direction for gradient fingerprints of tables too big to store (regenerated on the
+    GPU box from the formula; the golden-ratio stride keeps it aperiodic)."""
+    return np.cos(np.arange(n, dtype=np.float64) * 0.6180339887498949 + 0.25)
+
+
+def sample_entries(g: np.ndarray, n_top: int = 2048, n_nz: int = 4096, n_zero: int = 1024) -> np.ndarray:
+    """Entries of a big gradient to store element-wise: the largest ones, an even stride through the touched
+    ones and an even stride through the untouched ones (stray writes show up there)."""
+    a = np.abs(g)
+    nz = np.flatnonzero(a)
+    zz = np.flatnonzero(a == 0)
+    pick = [nz[np.argsort(a[nz])[-n_top:]]] if nz.size else []
+    if nz.size:
+        pick.append(nz[np.linspace(0, nz.size - 1, min(n_nz, nz.size)).astype(np.int64)])
+    if zz.size:
+        pick.append(zz[np.linspace(0, zz.size - 1, min(n_zero, zz.size)).astype(np.int64)])
+    return np.unique(np.concatenate(pick)) if pick else np.zeros(0, np.int64)
+
+
 def build_seeded(cfg: FieldConfig, seed: int, table_dtype: str = "fp16", **rand_kw) -> OracleLiDAR4D:
     """Deterministic model for a seed: constructor draws from torch's global CPU
     generator seeded here, then randomize_parameters() with its own generator."""

@@ -71,9 +71,38 @@ def to_np(d):
     return {k: v.detach().cpu().numpy() for k, v in d.items()}
 
 
-def run_case(name, time, n_rays_hw, num_steps, perturb, seed):
-    orc = oracle_for(SMALL, seed)
-    ref = build_reference(SMALL)
+FULL = dict(num_frames=51, near_lidar=0.0105, far_lidar=0.851)     # everything else = the reference's defaults
+BIG = 70000                                                         # gradients above this size are stored as samples
+
+
+def full_config(levels):
+    return FieldConfig(n_levels_hash=levels, **FULL)
+
+
+def build_reference_full(levels):
+    """The reference model with its own default tables (2^19 static, 2^15/2^13/2^13 dynamic, 2^18 flow)."""
+    tcnn_shim.install()
+    sys.path.insert(0, REF)
+    import model.hash_field as hf
+    import model.flow_field as ff
+    import model.lidar4d as l4d
+    l4d.HashGrid4D, l4d.FlowField = hf.HashGrid4D, ff.FlowField      # undo build_reference()'s small subclasses
+    return l4d.LiDAR4D(n_levels_hash=levels, **FULL)
+
+
+def run_case(name, time, n_rays_hw, num_steps, perturb, seed, levels=None):
+    """levels=None: the small-table configuration; levels=8/16: the full-size (benchmarked) configuration with
+    every MLP master weight snapped to an fp16-representable value (O.snap_mlp_weights_fp16), so that the
+    reference's fp32 arithmetic on the shim is at the same time the function the tensor-core kernels evaluate
+    with their fp16 working copies - one fixture pins both CUDA modes."""
+    full = levels is not None
+    if full:
+        orc = O.build_seeded(full_config(levels), seed, flow_last_std=0.02)
+        O.snap_mlp_weights_fp16(orc)
+        ref = build_reference_full(levels)
+    else:
+        orc = oracle_for(SMALL, seed)
+        ref = build_reference(SMALL)
     sd = orc.ref_state_dict()
     missing = ref.load_state_dict(sd, strict=False)
     assert all(k.startswith("unet") for k in missing.missing_keys), missing
@@ -156,9 +185,20 @@ def run_case(name, time, n_rays_hw, num_steps, perturb, seed):
         proj = rng.standard_normal(gv.shape[0])
         fx["gradnorm:" + k] = np.float64(np.linalg.norm(gv))
         fx["gradproj:" + k] = np.float64(gv @ proj)
-    small = {k: v for k, v in ref_grads.items() if v.numel() <= 12000}
+    small = {k: v for k, v in ref_grads.items() if v.numel() <= (BIG if full else 12000)}
     for k, g in small.items():
         fx["grad:" + k] = g.numpy().astype(np.float32)
+    if full:
+        fx["levels"] = levels
+        for k, g in ref_grads.items():
+            if g.numel() <= BIG:
+                continue
+            gv = g.double().numpy().reshape(-1)
+            fx["gradproj2:" + k] = np.float64(gv @ O.projection_vector(gv.shape[0]))
+            idx = O.sample_entries(g.numpy().reshape(-1))
+            fx["gradidx:" + k] = idx.astype(np.int32)
+            fx["gradval:" + k] = g.numpy().reshape(-1)[idx].astype(np.float32)
+        fx["ref_weights"] = out_ref["weights"].detach().numpy().astype(np.float32)
     # the parameters themselves are regenerated from the seed by
     # oracle.randomize_parameters; store a checksum so drift is detected
     fx["param_checksum"] = np.float64(sum(float(v.double().sum()) for v in sd.values()))
@@ -170,10 +210,14 @@ def run_case(name, time, n_rays_hw, num_steps, perturb, seed):
 def hash_index_vectors():
     """Known-answer uint32 hash indices for fixed points at every level of the
     three grid types (3D hashed, 2D hashed, 3D with a dense level 0), incl. edge
-    coordinates {0, 1, 1-eps, <0, >1}."""
+    coordinates {0, 1, 1-eps, <0, >1}; default L=8 geometry and the benchmarked
+    L=16 geometry (per_level_scale 2^(6/15): the top level lands on 32769 cells)."""
     cfg = FieldConfig()
+    cfg16 = FieldConfig(n_levels_hash=16)
     grids = {"static3d": cfg.static_grid(), "dyn2d_xy": cfg.dynamic_grid(0),
-             "dyn2d_xz": cfg.dynamic_grid(1), "flow3d": cfg.flow_grid()}
+             "dyn2d_xz": cfg.dynamic_grid(1), "flow3d": cfg.flow_grid(),
+             "static3d_L16": cfg16.static_grid(), "dyn2d_xy_L16": cfg16.dynamic_grid(0),
+             "dyn2d_yz_L16": cfg16.dynamic_grid(2)}
     g = torch.Generator().manual_seed(7)
     fx = {}
     for name, geo in grids.items():
@@ -182,6 +226,12 @@ def hash_index_vectors():
         edge = torch.tensor([[0.0] * D, [1.0] * D, [1.0 - 2 ** -24] * D, [-0.013] * D, [1.021] * D,
                              [0.5] * D, [-1.7] * D])
         x = torch.cat([x, edge], 0)
+        if name.endswith("_L16"):
+            # points whose finest-level position scale*x+0.5 sits on / next to an integer: the rounding cliff
+            sc = float(geo.scale[-1])
+            n = torch.randint(0, int(geo.resolution[-1]), (24, D), generator=g).double()
+            on = ((n - 0.5) / sc).float()
+            x = torch.cat([x, on, torch.nextafter(on, torch.ones_like(on)), torch.nextafter(on, -torch.ones_like(on))], 0)
         fx[name + ":x"] = x.numpy()
         fx[name + ":scale"] = geo.scale
         fx[name + ":resolution"] = geo.resolution
@@ -205,3 +255,8 @@ if __name__ == "__main__":
     run_case("ref_small_first", time=0.0, n_rays_hw=(3, 10), num_steps=40, perturb=False, seed=4)
     # last frame (no forward neighbour), with jitter
     run_case("ref_small_last", time=1.0, n_rays_hw=(3, 10), num_steps=40, perturb=True, seed=5)
+    # the benchmarked configuration (BASELINE.json configs[1]): default tables, S=768, jitter on
+    run_case("ref_full_L16_interior", time=7 / 50, n_rays_hw=(2, 8), num_steps=768, perturb=True, seed=21, levels=16)
+    run_case("ref_full_L8_interior", time=0.4, n_rays_hw=(2, 8), num_steps=768, perturb=True, seed=22, levels=8)
+    run_case("ref_full_L16_first", time=0.0, n_rays_hw=(2, 6), num_steps=768, perturb=False, seed=23, levels=16)
+    run_case("ref_full_L8_last", time=1.0, n_rays_hw=(2, 6), num_steps=768, perturb=True, seed=24, levels=8)

@@ -77,3 +77,33 @@ def relu_margin(oracle, stages) -> float:
         W1 = oracle.p("sigma_net.params")[:64 * c.sigma_in_pad].float().view(64, c.sigma_in_pad)
         ys = torch.cat([f, pad], -1) @ W1.t()
         return float(min(y1.abs().min(), y2.abs().min(), ys.abs().min()))
+
+
+# ---- the benchmarked (full-size) configuration ---------------------------------------------------------------------
+FULL = dict(num_frames=51, near_lidar=0.0105, far_lidar=0.851)
+
+
+def full_config(levels: int) -> FieldConfig:
+    """BASELINE.json configs[1]: the reference's default tables (2^19 static, 2^15/2^13/2^13 x 8 slices, 2^18 flow)."""
+    return FieldConfig(n_levels_hash=levels, **FULL)
+
+
+def full_oracle(levels: int, seed: int):
+    """Seeded full-size oracle whose MLP masters are fp16-representable (see O.snap_mlp_weights_fp16): the fp32-FMA and
+    the tensor-core kernels must both reproduce it, and tests/golden/ref_full_*.npz hold the unmodified reference's
+    results for exactly these parameters."""
+    from oracle import lidar4d_oracle as O
+    orc = O.build_seeded(full_config(levels), seed, flow_last_std=0.02)
+    return O.snap_mlp_weights_fp16(orc)
+
+
+def grad_errors(a, b):
+    """(max|a-b| / max|b|,  ||a-b|| / ||b||,  worst element-wise excess over 1e-3*|b| + 1e-5*max|b|)."""
+    a = torch.as_tensor(a).detach().double().reshape(-1).cpu()
+    b = torch.as_tensor(b).detach().double().reshape(-1).cpu()
+    if a.numel() == 0:
+        return 0.0, 0.0, 0.0
+    d = (a - b).abs()
+    bmax = float(b.abs().max()) + 1e-30
+    mixed = float((d - (1e-3 * b.abs() + 1e-5 * bmax)).max())
+    return float(d.max() / bmax), float(d.norm() / (b.norm() + 1e-30)), mixed

@@ -8,7 +8,7 @@ import torch
 
 from oracle import lidar4d_oracle as O
 from lidar4d_b200.geometry import FieldConfig
-from parity_util import small_config, rel_err
+from parity_util import small_config, rel_err, full_oracle
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CASES = ["ref_small_interior", "ref_small_first", "ref_small_last"]
@@ -18,14 +18,20 @@ def load(name):
     return np.load(os.path.join(GOLD, name + ".npz"))
 
 
+FULL_CASES = ["ref_full_L16_interior", "ref_full_L8_interior", "ref_full_L16_first", "ref_full_L8_last"]
+
+
 def oracle_case(fx):
-    orc = O.build_seeded(small_config(), int(fx["seed"]), flow_last_std=0.02)
+    if "levels" in fx.files:
+        orc = full_oracle(int(fx["levels"]), int(fx["seed"]))
+    else:
+        orc = O.build_seeded(small_config(), int(fx["seed"]), flow_last_std=0.02)
     chk = sum(float(v.double().sum()) for v in orc.ref_state_dict().values())
     assert abs(chk - float(fx["param_checksum"])) < 1e-6 * abs(float(fx["param_checksum"])), "seeded parameters drifted"
     return orc
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + FULL_CASES)
 def test_oracle_reproduces_reference_outputs(name):
     fx = load(name)
     orc = oracle_case(fx)
@@ -54,6 +60,13 @@ def test_oracle_reproduces_reference_outputs(name):
         assert abs(gv @ proj - p_ref) <= 2e-4 * max(n_ref * np.sqrt(gv.shape[0]) * 0.05, abs(p_ref)) + 1e-12, k
         if ("grad:" + k) in fx.files:
             assert rel_err(grads[k], fx["grad:" + k]) < 1e-4, k
+        if ("gradidx:" + k) in fx.files:          # full-size tables: sampled entries (largest / touched / untouched)
+            idx = fx["gradidx:" + k].astype(np.int64)
+            ref = fx["gradval:" + k]
+            assert np.abs(gv[idx] - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-30, k
+            assert np.all(gv[idx][ref == 0] == 0), k
+            p2 = float(fx["gradproj2:" + k])
+            assert abs(gv @ O.projection_vector(gv.shape[0]) - p2) <= 1e-4 * (abs(p2) + n_ref), k
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -67,9 +80,11 @@ def test_oracle_flow_matches_reference(name):
 
 def test_oracle_hash_indices_known_answers():
     fx = load("hash_indices")
-    cfg = FieldConfig()
+    cfg, cfg16 = FieldConfig(), FieldConfig(n_levels_hash=16)
     grids = {"static3d": cfg.static_grid(), "dyn2d_xy": cfg.dynamic_grid(0), "dyn2d_xz": cfg.dynamic_grid(1),
-             "flow3d": cfg.flow_grid()}
+             "flow3d": cfg.flow_grid(), "static3d_L16": cfg16.static_grid(), "dyn2d_xy_L16": cfg16.dynamic_grid(0),
+             "dyn2d_yz_L16": cfg16.dynamic_grid(2)}
+    assert int(cfg16.static_grid().resolution[-1]) == 32769      # the L=16 rounding cliff
     for name, geo in grids.items():
         # geometry itself is data: it must be reproduced bit-exactly on this machine
         assert np.array_equal(geo.resolution, fx[name + ":resolution"])
