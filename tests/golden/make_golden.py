@@ -119,14 +119,20 @@ def run_case(name, time, n_rays_hw, num_steps, perturb, seed, levels=None):
 
     # the reference draws jitter from torch.rand (renderer.py:84): feed it the
     # repo's counter-based stream so the perturbed case is reproducible
-    orig_rand = torch.rand
+    orig_rand, orig_linspace = torch.rand, torch.linspace
     if perturb:
         u = torch.from_numpy(O.jitter_uniform(seed, np.arange(N), num_steps))
         torch.rand = lambda *a, **k: u.clone()
+    if full:
+        # The reference runs on CUDA, where torch.linspace(0,1,S) (renderer.py:69) rounds 62 of 768 points differently
+        # from the CPU kernel; at the finest hash level (32769 cells, white-noise tables) one ulp of z moves sigma by
+        # ~2e-3.  Feed the reference the CUDA grid (O.sample_lin restates it; tests/test_gpu_fullsize_parity.py pins
+        # that restatement bit-exactly against torch.linspace(device="cuda") on the GPU box).
+        torch.linspace = lambda a, b, n, **k: torch.from_numpy(O.sample_lin(n)) if (a, b) == (0.0, 1.0) else orig_linspace(a, b, n, **k)
     try:
         out_ref = ref.render(rays_o, rays_d, t, staged=False, num_steps=num_steps, perturb=perturb)
     finally:
-        torch.rand = orig_rand
+        torch.rand, torch.linspace = orig_rand, orig_linspace
     g_depth = torch.linspace(0.5, 1.5, N).view(1, N)
     g_image = torch.stack([torch.linspace(-1, 1, N), torch.linspace(1, 0.2, N)], -1).view(1, N, 2)
     loss = (out_ref["depth_lidar"] * g_depth).sum() + (out_ref["image_lidar"] * g_image).sum()
@@ -136,7 +142,7 @@ def run_case(name, time, n_rays_hw, num_steps, perturb, seed, levels=None):
 
     # the reference's z grid comes from the CPU torch.linspace; hand the oracle
     # the identical grid so this comparison isolates the model arithmetic
-    lin = torch.linspace(0.0, 1.0, num_steps).numpy()
+    lin = O.sample_lin(num_steps) if full else torch.linspace(0.0, 1.0, num_steps).numpy()
     out_orc = orc.render(rays_o[0], rays_d[0], time, num_steps=num_steps, perturb=perturb, seed=seed,
                          lin=lin, return_stages=True)
     loss_o = (out_orc["depth_lidar"] * g_depth[0]).sum() + (out_orc["image_lidar"] * g_image[0]).sum()

@@ -62,6 +62,13 @@ def cuda_run(fx, orc, dev, mode, pipeline, scale=1.0, autocast=False):
     return m, out, {k: p.grad for k, p in m.named_parameters()}
 
 
+@pytest.mark.parametrize("S", [768, 767, 129, 2, 1000])
+def test_z_grid_matches_cuda_linspace(dev, S):
+    """The kernel's / oracle's restatement of torch.linspace(0,1,S) on CUDA (renderer.py:69; the reference renders on
+    the GPU) is bit-exact - the full-size goldens were generated on this grid."""
+    assert np.array_equal(torch.linspace(0.0, 1.0, S, device=dev).cpu().numpy(), O.sample_lin(S))
+
+
 def test_hash_indices_bit_exact_L16(dev):
     from lidar4d_b200 import LiDAR4D
     fx = np.load(os.path.join(GOLD, "hash_indices.npz"))

@@ -36,7 +36,8 @@ def test_oracle_reproduces_reference_outputs(name):
     fx = load(name)
     orc = oracle_case(fx)
     S = int(fx["num_steps"])
-    lin = torch.linspace(0.0, 1.0, S).numpy()          # the reference's CPU z grid (renderer.py:69)
+    # small cases: the reference's CPU z grid (renderer.py:69); full-size cases were generated on the CUDA grid
+    lin = O.sample_lin(S) if "levels" in fx.files else torch.linspace(0.0, 1.0, S).numpy()
     out = orc.render(torch.from_numpy(fx["rays_o"]), torch.from_numpy(fx["rays_d"]), float(fx["time"]),
                      num_steps=S, perturb=bool(fx["perturb"]), seed=int(fx["seed"]), lin=lin)
     assert rel_err(out["depth_lidar"], fx["ref_depth_lidar"]) < 1e-5
