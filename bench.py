@@ -288,7 +288,8 @@ def run_b200(args):
     model.pipeline = args.pipeline
     model.set_mlp_fp16(args.mlp == "fp16")
     dp = RayShardedDP(model, world_size=world, rank=rank)
-    opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True)
+    from lidar4d_b200.optim import Adam          # main_lidar4d.py:298-300 recipe, one launch fused with the fp16 table refresh
+    opt = Adam(model, model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
     n_rays, rb = args.rays, args.ray_batch
 
     # host-side inputs in pinned memory (one sweep per frame), targets on the host as well
@@ -321,7 +322,6 @@ def run_b200(args):
                 outs.append(torch.cat([out["depth_lidar"].detach().view(-1, 1), out["image_lidar"].detach().view(-1, 2)], 1))
         dp.allreduce_grads()
         opt.step()
-        model._engine.ensure_staged()
         if e2e:
             host_out.copy_(torch.cat(outs, 0), non_blocking=True)
             return float(tot)            # device->host read of the step's loss (sync)

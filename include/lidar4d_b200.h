@@ -152,6 +152,35 @@ size_t l4d_staged_bytes(const L4DConfig* cfg);
 int    l4d_stage_params(const L4DConfig* cfg, const L4DMasterParams* master,
                         void* staged, size_t staged_bytes, void* stream);
 
+/* Same, selectively: L4D_STAGE_TABLES = the three hash-table groups (fp16 casts / slice-pair packing),
+ * L4D_STAGE_SMALL = planes (channels-last), MLP working copies and tensor-core operand copies - ONE launch for all of
+ * them.  `staged` must have been zero-filled once when it was allocated (operand padding is never rewritten).
+ * After l4d_adam_step with a `master` table only L4D_STAGE_SMALL is left to do. */
+#define L4D_STAGE_TABLES 1u
+#define L4D_STAGE_SMALL  2u
+int    l4d_stage_params_ex(const L4DConfig* cfg, const L4DMasterParams* master,
+                           void* staged, size_t staged_bytes, uint32_t what, void* stream);
+
+/* --- optimiser step (replaces torch.optim.Adam of main_lidar4d.py:298-300 + the re-staging pass) -----
+ * Adam (no weight decay, no amsgrad; torch's fused-kernel operation order) over FLAT fp32 arenas: params, grads and the
+ * two moment buffers hold every tensor of the hot path at the same offsets (each tensor starts on a multiple of
+ * L4D_ADAM_CHUNK floats).  `groups` = sorted, disjoint [begin,end) float ranges with their learning rate (the
+ * reference's param groups, lidar4d.py:226-237); ranges not covered are left alone.  grads are multiplied by inv_scale
+ * (1/loss-scale) on the fly; zero_grad=1 clears them in the same pass.  If `master` is given (pointers INTO `params`),
+ * a group that is exactly one hash table also emits that table's fp16 working copy into `staged` (static / flow: cast;
+ * dynamic slice t: the lo half of pair t and the hi half of pair t-1), i.e. l4d_stage_params_ex(L4D_STAGE_TABLES) for free. */
+#define L4D_ADAM_CHUNK 1024
+#define L4D_ADAM_MAX_SEGMENTS 64
+typedef struct L4DAdamGroup {
+  uint64_t begin, end;     /* floats, relative to the arena start; begin % L4D_ADAM_CHUNK == 0, end % 4 == 0 */
+  float    lr;
+  uint32_t reserved;
+} L4DAdamGroup;
+int    l4d_adam_step(const L4DConfig* cfg, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                     uint64_t n_floats, const L4DAdamGroup* groups, uint32_t n_groups,
+                     float beta1, float beta2, float eps, uint32_t step, float inv_scale, uint32_t zero_grad,
+                     const L4DMasterParams* master_or_null, void* staged_or_null, size_t staged_bytes, void* stream);
+
 /* --- LiDAR_Renderer.run forward (renderer.py:44-140 + lidar4d.py:139-223), one fused kernel.
  *     depth[n], image[n,2] (ch0 raydrop, ch1 intensity), wsum[n]; weights/z_vals [n,S] optional.
  *     `saved` (l4d_saved_bytes) enables a later backward; NULL = inference. ------------------- */
@@ -218,6 +247,8 @@ int    l4d_chamfer_backward(const float* xyz1, const float* xyz2, uint32_t b, ui
 /* --- profiling aid: while started, CUDA events are recorded on the launch stream around every kernel of
  *     l4d_render_forward / l4d_render_backward.  l4d_profile_stop returns the number of (kernel name, ms)
  *     pairs written (static strings), or a negative error code.  Not thread-safe. --------------------------- */
+/* kernels this library has launched in this process so far (bench.py "gpu_launches"; counted at the launch sites). */
+unsigned long long l4d_launch_count(void);
 int    l4d_profile_start(void);
 int    l4d_profile_stop(const char** names, float* ms, int cap);
 

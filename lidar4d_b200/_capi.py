@@ -14,6 +14,8 @@ MAX_LEVELS = 16
 MAX_PLANE_SCALES = 4
 MAX_TIME_SLICES = 16
 ABI_VERSION = 1
+STAGE_TABLES, STAGE_SMALL = 1, 2        # l4d_stage_params_ex `what`
+ADAM_CHUNK, ADAM_MAX_SEGMENTS = 1024, 64
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -59,6 +61,10 @@ class L4DMasterParams(C.Structure):
 
 class L4DMasterGrads(C.Structure):
     _fields_ = L4DMasterParams._fields_
+
+
+class L4DAdamGroup(C.Structure):
+    _fields_ = [("begin", C.c_uint64), ("end", C.c_uint64), ("lr", C.c_float), ("reserved", C.c_uint32)]
 
 
 class L4DRays(C.Structure):
@@ -139,6 +145,7 @@ EXPORTS = [
     "l4d_abi_version", "l4d_last_error", "l4d_staged_bytes", "l4d_stage_params", "l4d_saved_bytes",
     "l4d_render_forward", "l4d_grad_work_bytes", "l4d_render_backward", "l4d_unstage_grads",
     "l4d_flow_forward", "l4d_flow_backward", "l4d_hash_indices", "l4d_density_forward", "l4d_attribute_forward", "l4d_chamfer_work_bytes", "l4d_chamfer_forward", "l4d_chamfer_backward", "l4d_tc_selftest", "l4d_tc_selftest2", "l4d_profile_start", "l4d_profile_stop",
+    "l4d_stage_params_ex", "l4d_adam_step", "l4d_launch_count",
 ]
 
 
@@ -184,6 +191,13 @@ def declare(lib, prefix: str = "l4d_", host_sim: bool = False):
         lib.l4d_tc_selftest.restype = C.c_int
         lib.l4d_tc_selftest2.argtypes = [V, V, V, U32, U32, U32, U32, U32, V]
         lib.l4d_tc_selftest2.restype = C.c_int
+        lib.l4d_stage_params_ex.argtypes = [P(L4DConfig), P(L4DMasterParams), V, SZ, U32, V]
+        lib.l4d_stage_params_ex.restype = C.c_int
+        lib.l4d_adam_step.argtypes = [P(L4DConfig), V, V, V, V, C.c_uint64, P(L4DAdamGroup), U32, C.c_float, C.c_float,
+                                      C.c_float, U32, C.c_float, U32, P(L4DMasterParams), V, SZ, V]
+        lib.l4d_adam_step.restype = C.c_int
+        lib.l4d_launch_count.argtypes = []
+        lib.l4d_launch_count.restype = C.c_uint64
         lib.l4d_profile_start.argtypes = []
         lib.l4d_profile_start.restype = C.c_int
         lib.l4d_profile_stop.argtypes = [P(C.c_char_p), P(C.c_float), C.c_int]

@@ -166,12 +166,12 @@ static int nn_one_direction(const float* q, uint32_t nq, const float* t, uint32_
   const uint32_t s = splits_for(b, nq, nt);
   const dim3 grid(qblocks, s, b);
   if (s == 1) {
-    k_chamfer_nn<true><<<grid, CH_NT, 0, st>>>(q, nq, t, nt, dist, idx, nullptr);
+    ++g_launches; k_chamfer_nn<true><<<grid, CH_NT, 0, st>>>(q, nq, t, nt, dist, idx, nullptr);
   } else {
     const size_t n = (size_t)b * nq;
-    k_chamfer_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n);
-    k_chamfer_nn<false><<<grid, CH_NT, 0, st>>>(q, nq, t, nt, nullptr, nullptr, keys);
-    k_chamfer_unpack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, dist, idx);
+    ++g_launches; k_chamfer_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n);
+    ++g_launches; k_chamfer_nn<false><<<grid, CH_NT, 0, st>>>(q, nq, t, nt, nullptr, nullptr, keys);
+    ++g_launches; k_chamfer_unpack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, dist, idx);
   }
   return 0;
 }
@@ -207,8 +207,8 @@ extern "C" int l4d_chamfer_backward(const float* xyz1, const float* xyz2, uint32
   if (n == 0 || m == 0) return l4d_fail(L4D_EINVAL, "chamfer: empty point cloud");
   if (b > 65535u) return l4d_fail(L4D_EINVAL, "chamfer: batch too large");
   cudaStream_t st = (cudaStream_t)stream;
-  k_chamfer_grad<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, xyz1, m, xyz2, g_dist1, idx1, g_xyz1, g_xyz2);
-  k_chamfer_grad<<<dim3((m + 255) / 256, b), 256, 0, st>>>(m, xyz2, n, xyz1, g_dist2, idx2, g_xyz2, g_xyz1);
+  ++g_launches; k_chamfer_grad<<<dim3((n + 255) / 256, b), 256, 0, st>>>(n, xyz1, m, xyz2, g_dist1, idx1, g_xyz1, g_xyz2);
+  ++g_launches; k_chamfer_grad<<<dim3((m + 255) / 256, b), 256, 0, st>>>(m, xyz2, n, xyz1, g_dist2, idx2, g_xyz2, g_xyz1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "chamfer backward: %s", cudaGetErrorString(e));
   return L4D_OK;

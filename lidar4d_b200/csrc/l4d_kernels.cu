@@ -5,6 +5,7 @@
 // Reference path replaced: model/renderer.py:44-140 (LiDAR_Renderer.run),
 // model/lidar4d.py:124-223 (flow/density/attribute) and the encoders under it.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -12,11 +13,13 @@
 #include "l4d_core.cuh"
 #include "l4d_host.h"
 #include "l4d_tc.cuh"
+#include "l4d_optim.cuh"
 
 // =============================================================================
 // error plumbing
 // =============================================================================
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
 int l4d_fail(int code, const char* fmt, const char* a, const char* b) {
   snprintf(g_err, sizeof(g_err), fmt, a, b);
   return code;
@@ -59,6 +62,9 @@ extern "C" int l4d_profile_stop(const char** names, float* ms, int cap) {
   g_prof_n = 0;
   return n;
 }
+
+// kernels launched by this library in this process (bench "gpu_launches"; counted where they are launched)
+extern "C" unsigned long long l4d_launch_count(void) { return g_launches; }
 
 extern "C" int l4d_abi_version(void) { return L4D_ABI_VERSION; }
 extern "C" const char* l4d_last_error(void) { return g_err; }
@@ -176,6 +182,7 @@ __global__ void k_pack_umma(const float* __restrict__ W, int ld, int n_rows, int
   dst[((size_t)(k >> 3) * rows_total + row_off + n) * 8 + (k & 7)] = __float2half_rn(__ldg(W + (size_t)n * ld + k0 + k));
 }
 
+static int sm_count();
 static inline int nblk(size_t n, int t = 256) { return (int)((n + t - 1) / t); }
 
 extern "C" size_t l4d_staged_bytes(const L4DConfig* cfg) {
@@ -183,8 +190,14 @@ extern "C" size_t l4d_staged_bytes(const L4DConfig* cfg) {
   return staged_layout(cfg).total;
 }
 
-extern "C" int l4d_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, void* staged, size_t staged_bytes,
-                                void* stream) {
+static inline StageJob make_job(int type, const float* src, void* dst, int n, int a = 0, int b = 0, int c = 0, int d = 0, int e = 0, int round16 = 0) {
+  StageJob j;
+  j.src = src; j.dst = dst; j.type = type; j.n = n; j.a = a; j.b = b; j.c = c; j.d = d; j.e = e; j.round16 = round16;
+  return j;
+}
+
+extern "C" int l4d_stage_params_ex(const L4DConfig* cfg, const L4DMasterParams* m, void* staged, size_t staged_bytes,
+                                   uint32_t what, void* stream) {
   int rc = check_config(cfg);
   if (rc != L4D_OK) return rc;
   if (!m || !staged) return l4d_fail(L4D_EINVAL, "null pointer");
@@ -194,66 +207,163 @@ extern "C" int l4d_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, 
   char* b = reinterpret_cast<char*>(staged);
   auto H = [&](size_t off) { return reinterpret_cast<__half*>(b + off); };
   auto F = [&](size_t off) { return reinterpret_cast<float*>(b + off); };
-  {
-    size_t n = (size_t)cfg->hash_static.offset[cfg->hash_static.n_levels] * 4;
-    k_cast_half<<<2048, 256, 0, st>>>(m->hash_static, H(L.hs), n);
-  }
-  for (int p = 0; p < 3; ++p) {
-    const size_t ne = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels];
-    for (uint32_t s = 0; s < cfg->time_resolution; ++s)
-      if (!m->hash_dynamic[p][s]) return l4d_fail(L4D_EINVAL, "null hash_dynamic slice");
-    for (uint32_t s = 0; s + 1 < cfg->time_resolution; ++s)
-      k_pack_pair<<<512, 256, 0, st>>>(m->hash_dynamic[p][s], m->hash_dynamic[p][s + 1],
-                                        reinterpret_cast<uint4*>(b + L.hd[p]) + (size_t)s * ne, ne);
-  }
-  {
-    size_t n = (size_t)cfg->flow.offset[cfg->flow.n_levels] * 8;
-    k_cast_half<<<2048, 256, 0, st>>>(m->flow_grid, H(L.hf), n);
-  }
-  for (uint32_t s = 0; s < cfg->n_plane_scales; ++s)
-    for (int ci = 0; ci < 6; ++ci) {
-      int Hh, W;
-      plane_hw(cfg, s, ci, Hh, W);
-      k_plane_to_cl<<<nblk((size_t)Hh * W * 8), 256, 0, st>>>(m->planes[s][ci], F(L.planes[s][ci]), Hh * W);
+  if (what & L4D_STAGE_TABLES) {
+    {
+      size_t n = (size_t)cfg->hash_static.offset[cfg->hash_static.n_levels] * 4;
+      ++g_launches; k_cast_half<<<2048, 256, 0, st>>>(m->hash_static, H(L.hs), n);
     }
-  // sigma net: params = [64][in_pad] | [16][64]
-  const int ip = (int)cfg->sigma_in_pad;
-  k_transpose<<<nblk((size_t)ip * 64), 256, 0, st>>>(m->sigma_net, ip, F(L.sig_w1t), ip, 64, ip, 64);
-  k_transpose<<<nblk(64 * 16), 256, 0, st>>>(m->sigma_net + 64 * ip, 64, F(L.sig_w2t), 64, 16, 64, 16);
-  k_copy_block<<<nblk(16 * 64), 256, 0, st>>>(m->sigma_net + 64 * ip, F(L.sig_w2), 16 * 64, 16 * 64);
-  // attribute nets: [64][96] | [64][64] | [16][64]; image channel 0 = raydrop, 1 = intensity (lidar4d.py:216)
-  const float* att[2] = {m->raydrop_net, m->intensity_net};
-  const int ap = (int)cfg->attr_in_pad;
-  for (int n = 0; n < 2; ++n) {
-    k_transpose<<<nblk((size_t)ap * 64), 256, 0, st>>>(att[n], ap, F(L.att_w1t[n]), ap, 64, ap, 64);
-    k_transpose<<<nblk(64 * 64), 256, 0, st>>>(att[n] + 64 * ap, 64, F(L.att_w2t[n]), 64, 64, 64, 64);
-    k_copy_block<<<nblk(64 * 64), 256, 0, st>>>(att[n] + 64 * ap, F(L.att_w2[n]), 64 * 64, 64 * 64);
-    k_copy_block<<<1, 64, 0, st>>>(att[n] + 64 * ap + 64 * 64, F(L.att_w3[n]), 64, 64);
+    for (int p = 0; p < 3; ++p) {
+      const size_t ne = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels];
+      for (uint32_t s = 0; s < cfg->time_resolution; ++s)
+        if (!m->hash_dynamic[p][s]) return l4d_fail(L4D_EINVAL, "null hash_dynamic slice");
+      for (uint32_t s = 0; s + 1 < cfg->time_resolution; ++s) {
+        ++g_launches;
+        k_pack_pair<<<512, 256, 0, st>>>(m->hash_dynamic[p][s], m->hash_dynamic[p][s + 1],
+                                          reinterpret_cast<uint4*>(b + L.hd[p]) + (size_t)s * ne, ne);
+      }
+    }
+    {
+      size_t n = (size_t)cfg->flow.offset[cfg->flow.n_levels] * 8;
+      ++g_launches; k_cast_half<<<2048, 256, 0, st>>>(m->flow_grid, H(L.hf), n);
+    }
   }
-  // flow MLP: [64][16], [64][64], [6][64]
-  k_transpose<<<nblk(16 * 64), 256, 0, st>>>(m->flow_mlp[0], 16, F(L.flo_w0t), 16, 64, 16, 64);
-  k_transpose<<<nblk(64 * 64), 256, 0, st>>>(m->flow_mlp[1], 64, F(L.flo_w1t), 64, 64, 64, 64);
-  k_copy_block<<<nblk(64 * 64), 256, 0, st>>>(m->flow_mlp[1], F(L.flo_w1), 64 * 64, 64 * 64);
-  k_transpose<<<nblk(64 * 8), 256, 0, st>>>(m->flow_mlp[2], 64, F(L.flo_w2t), 64, 8, 64, 6);
-  k_copy_block<<<nblk(8 * 64), 256, 0, st>>>(m->flow_mlp[2], F(L.flo_w2), 6 * 64, 8 * 64);
-  if (cfg->mlp_fp16) {
-    // every fp32 MLP working copy becomes fp16-representable (one rounding, shared by FMA and tensor-core paths)
-    const size_t lo = L.sig_w1t, hi = L.tc_sig_w1;
-    k_round_fp16<<<nblk((hi - lo) / 4), 256, 0, st>>>(F(lo), (int)((hi - lo) / 4));
+  if (what & L4D_STAGE_SMALL) {
+    // planes, MLP working copies (both orientations) and tensor-core operand copies: one launch, one job each
+    JobArgs J;
+    int nj = 0;
+    auto add = [&](const StageJob& j) { if (nj < L4D_MAX_JOBS) J.job[nj] = j; ++nj; };
+    int maxn = 0;
+    for (uint32_t s = 0; s < cfg->n_plane_scales; ++s)
+      for (int ci = 0; ci < 6; ++ci) {
+        int Hh, W;
+        plane_hw(cfg, s, ci, Hh, W);
+        add(make_job(L4D_JOB_PLANE_TO_CL, m->planes[s][ci], F(L.planes[s][ci]), Hh * W * 8, Hh * W));
+      }
+    const int r16 = cfg->mlp_fp16 ? 1 : 0;   // fp32 working copies become fp16-representable (as tcnn holds its weights)
+    auto T = [&](const float* src, int src_ld, size_t dst, int dst_rows, int dst_cols, int vr, int vc) {
+      add(make_job(L4D_JOB_TRANSPOSE, src, F(dst), dst_rows * dst_cols, src_ld, dst_cols, vr, vc, 0, r16));
+    };
+    auto Cp = [&](const float* src, size_t dst, int n_valid, int n_total) {
+      add(make_job(L4D_JOB_COPY, src, F(dst), n_total, n_valid, 0, 0, 0, 0, r16));
+    };
+    auto U = [&](const float* W, int ld, int n_rows, int k0, int K, size_t dst, int rows_total, int row_off) {
+      add(make_job(L4D_JOB_PACK_UMMA, W, H(dst), n_rows * K, ld, K, k0, rows_total, row_off));
+    };
+    // sigma net: params = [64][in_pad] | [16][64]
+    const int ip = (int)cfg->sigma_in_pad;
+    T(m->sigma_net, ip, L.sig_w1t, ip, 64, ip, 64);
+    T(m->sigma_net + 64 * ip, 64, L.sig_w2t, 64, 16, 64, 16);
+    Cp(m->sigma_net + 64 * ip, L.sig_w2, 16 * 64, 16 * 64);
+    // attribute nets: [64][96] | [64][64] | [16][64]; image channel 0 = raydrop, 1 = intensity (lidar4d.py:216)
+    const float* att[2] = {m->raydrop_net, m->intensity_net};
+    const int ap = (int)cfg->attr_in_pad;
+    for (int n = 0; n < 2; ++n) {
+      T(att[n], ap, L.att_w1t[n], ap, 64, ap, 64);
+      T(att[n] + 64 * ap, 64, L.att_w2t[n], 64, 64, 64, 64);
+      Cp(att[n] + 64 * ap, L.att_w2[n], 64 * 64, 64 * 64);
+      Cp(att[n] + 64 * ap + 64 * 64, L.att_w3[n], 64, 64);
+    }
+    // flow MLP: [64][16], [64][64], [6][64]
+    T(m->flow_mlp[0], 16, L.flo_w0t, 16, 64, 16, 64);
+    T(m->flow_mlp[1], 64, L.flo_w1t, 64, 64, 64, 64);
+    Cp(m->flow_mlp[1], L.flo_w1, 64 * 64, 64 * 64);
+    T(m->flow_mlp[2], 64, L.flo_w2t, 64, 8, 64, 6);
+    Cp(m->flow_mlp[2], L.flo_w2, 6 * 64, 8 * 64);
+    // tensor-core operand copies (fp16, UMMA no-swizzle K-major layout).  Rows / columns these jobs never write
+    // (tc_att_w1g column 15, tc_flo_w2 rows 6..15) must be zero: the caller zero-fills `staged` once at allocation.
+    U(m->sigma_net, ip, 64, 0, ip, L.tc_sig_w1, 64, 0);
+    U(m->sigma_net + 64 * ip, 64, 16, 0, 64, L.tc_sig_w2, 16, 0);
+    for (int n = 0; n < 2; ++n) {
+      U(att[n], ap, 64, L4D_ENC, 15, L.tc_att_w1g, 128, n * 64);
+      U(att[n] + 64 * ap, 64, 64, 0, 64, L.tc_att_w2[n], 64, 0);
+      U(att[n], ap, 64, L4D_ENC, 16, L.tc_att_w1g_net[n], 64, 0);
+    }
+    U(m->flow_mlp[0], 16, 64, 0, 16, L.tc_flo_w0, 64, 0);
+    U(m->flow_mlp[1], 64, 64, 0, 64, L.tc_flo_w1, 64, 0);
+    U(m->flow_mlp[2], 64, 6, 0, 64, L.tc_flo_w2, 16, 0);
+    if (nj > L4D_MAX_JOBS) return l4d_fail(L4D_EINVAL, "too many staging jobs");
+    J.n_jobs = nj;
+    for (int i = 0; i < nj; ++i) maxn = J.job[i].n > maxn ? J.job[i].n : maxn;
+    int gx = (maxn + 256 * 8 - 1) / (256 * 8);
+    if (gx < 1) gx = 1;
+    ++g_launches; k_stage_jobs<<<dim3(gx, nj), 256, 0, st>>>(J);
   }
-  // tensor-core operand copies
-  k_pack_umma<<<nblk((size_t)64 * ip), 256, 0, st>>>(m->sigma_net, ip, 64, 0, ip, H(L.tc_sig_w1), 64, 0);
-  k_pack_umma<<<nblk(16 * 64), 256, 0, st>>>(m->sigma_net + 64 * ip, 64, 16, 0, 64, H(L.tc_sig_w2), 16, 0);
-  cudaMemsetAsync(b + L.tc_att_w1g, 0, 16 * 128 * 2, st);
-  for (int n = 0; n < 2; ++n) {
-    k_pack_umma<<<nblk(64 * 15), 256, 0, st>>>(att[n], ap, 64, L4D_ENC, 15, H(L.tc_att_w1g), 128, n * 64);
-    k_pack_umma<<<nblk(64 * 64), 256, 0, st>>>(att[n] + 64 * ap, 64, 64, 0, 64, H(L.tc_att_w2[n]), 64, 0);
-    k_pack_umma<<<nblk(64 * 16), 256, 0, st>>>(att[n], ap, 64, L4D_ENC, 16, H(L.tc_att_w1g_net[n]), 64, 0);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+extern "C" int l4d_stage_params(const L4DConfig* cfg, const L4DMasterParams* m, void* staged, size_t staged_bytes,
+                                void* stream) {
+  // the operand-copy padding must be zero; callers of the _ex variant zero-fill once, this entry point does it per call
+  if (cfg && staged && check_config(cfg) == L4D_OK) {
+    StagedLayout L = staged_layout(cfg);
+    if (staged_bytes >= L.total) {
+      char* b = reinterpret_cast<char*>(staged);
+      cudaMemsetAsync(b + L.tc_att_w1g, 0, 16 * 128 * 2, (cudaStream_t)stream);
+      cudaMemsetAsync(b + L.tc_flo_w2, 0, 64 * 16 * 2, (cudaStream_t)stream);
+    }
   }
-  k_pack_umma<<<nblk(64 * 16), 256, 0, st>>>(m->flow_mlp[0], 16, 64, 0, 16, H(L.tc_flo_w0), 64, 0);
-  k_pack_umma<<<nblk(64 * 64), 256, 0, st>>>(m->flow_mlp[1], 64, 64, 0, 64, H(L.tc_flo_w1), 64, 0);
-  cudaMemsetAsync(b + L.tc_flo_w2, 0, 64 * 16 * 2, st);
-  k_pack_umma<<<nblk(6 * 64), 256, 0, st>>>(m->flow_mlp[2], 64, 6, 0, 64, H(L.tc_flo_w2), 16, 0);
+  return l4d_stage_params_ex(cfg, m, staged, staged_bytes, L4D_STAGE_TABLES | L4D_STAGE_SMALL, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Adam over the flat arenas, fused with the fp16 refresh of the hash tables (l4d_optim.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int l4d_adam_step(const L4DConfig* cfg, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                             uint64_t n_floats, const L4DAdamGroup* groups, uint32_t n_groups, float beta1, float beta2,
+                             float eps, uint32_t step, float inv_scale, uint32_t zero_grad, const L4DMasterParams* master,
+                             void* staged, size_t staged_bytes, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != L4D_OK) return rc;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !groups) return l4d_fail(L4D_EINVAL, "null pointer");
+  if (n_groups < 1 || n_groups > L4D_ADAM_MAX_SEGMENTS) return l4d_fail(L4D_EINVAL, "1..64 Adam groups");
+  if (n_floats % L4D_ADAM_CHUNK || step < 1) return l4d_fail(L4D_EINVAL, "arena size must be a multiple of 1024 floats, step >= 1");
+  if ((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15)) return l4d_fail(L4D_EINVAL, "arenas must be 16-byte aligned");
+  AdamArgs A;
+  memset(&A, 0, sizeof(A));
+  A.p = params; A.g = grads; A.g_rw = grads; A.m = exp_avg; A.v = exp_avg_sq;
+  A.n_chunks = n_floats / L4D_ADAM_CHUNK;
+  A.beta1 = beta1; A.beta2 = beta2; A.eps = eps; A.inv_scale = inv_scale; A.zero_grad = zero_grad;
+  A.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  A.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  A.n_seg = (int)n_groups;
+  StagedLayout L;
+  char* sb = reinterpret_cast<char*>(staged);
+  if (master) {
+    if (!staged) return l4d_fail(L4D_EINVAL, "master given without a staged buffer");
+    L = staged_layout(cfg);
+    if (staged_bytes < L.total) return l4d_fail(L4D_ESIZE, "staged buffer too small");
+  }
+  unsigned long long prev_end = 0;
+  for (uint32_t i = 0; i < n_groups; ++i) {
+    AdamSeg& s = A.seg[i];
+    s.begin = groups[i].begin; s.end = groups[i].end; s.lr = groups[i].lr;
+    if (s.begin % L4D_ADAM_CHUNK || s.end <= s.begin || s.end > n_floats || s.begin < prev_end || (s.end & 3))
+      return l4d_fail(L4D_EINVAL, "Adam groups must be sorted, disjoint, start on multiples of 1024 floats and end on multiples of 4");
+    prev_end = s.end;
+    if (!master) continue;
+    const float* gp = params + s.begin;
+    const unsigned long long len = s.end - s.begin;
+    if (gp == master->hash_static && len == (unsigned long long)cfg->hash_static.offset[cfg->hash_static.n_levels] * 4) {
+      s.dst0 = reinterpret_cast<unsigned char*>(sb + L.hs); s.stride0 = 8;
+    } else if (gp == master->flow_grid && len == (unsigned long long)cfg->flow.offset[cfg->flow.n_levels] * 8) {
+      s.dst0 = reinterpret_cast<unsigned char*>(sb + L.hf); s.stride0 = 8;
+    } else {
+      for (int p = 0; p < 3; ++p) {
+        const unsigned long long ne = cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels];
+        for (uint32_t t = 0; t < cfg->time_resolution; ++t) {
+          if (gp != master->hash_dynamic[p][t] || len != ne * 4) continue;
+          unsigned char* base = reinterpret_cast<unsigned char*>(sb + L.hd[p]);        // pair k = slices k, k+1: {lo 4 halves | hi 4 halves}
+          if (t + 1 < cfg->time_resolution) { s.dst0 = base + (size_t)t * ne * 16; s.stride0 = 16; s.off0 = 0; }
+          if (t > 0) { s.dst1 = base + (size_t)(t - 1) * ne * 16; s.stride1 = 16; s.off1 = 8; }
+        }
+      }
+    }
+  }
+  unsigned long long blocks = A.n_chunks;
+  const unsigned long long cap = (unsigned long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  ++g_launches; k_adam_flat<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -273,27 +383,38 @@ extern "C" int l4d_unstage_grads(const L4DConfig* cfg, const void* grad_work, si
   cudaStream_t st = (cudaStream_t)stream;
   const char* b = reinterpret_cast<const char*>(grad_work);
   auto F = [&](size_t off) { return reinterpret_cast<const float*>(b + off); };
+  JobArgs J;
+  int nj = 0, maxn = 0;
+  auto add = [&](int type, size_t src, float* dst, int n, int a = 0, int bb = 0) {
+    if (!dst) return;
+    if (nj < L4D_MAX_JOBS) J.job[nj] = make_job(type, F(src), dst, n, a, bb);
+    ++nj;
+    maxn = n > maxn ? n : maxn;
+  };
   for (uint32_t s = 0; s < cfg->n_plane_scales; ++s)
     for (int ci = 0; ci < 6; ++ci) {
       int Hh, W;
       plane_hw(cfg, s, ci, Hh, W);
-      if (g->planes[s][ci]) k_plane_from_cl<<<nblk((size_t)Hh * W * 8), 256, 0, st>>>(F(L.planes[s][ci]), g->planes[s][ci], Hh * W);
+      add(L4D_JOB_PLANE_FROM_CL, L.planes[s][ci], g->planes[s][ci], Hh * W * 8, Hh * W);
     }
   const int ip = (int)cfg->sigma_in_pad, ap = (int)cfg->attr_in_pad;
-  if (g->sigma_net) {
-    k_add_transposed<<<nblk((size_t)64 * ip), 256, 0, st>>>(F(L.sig_w1t), 64, g->sigma_net, 64, ip);
-    k_add<<<nblk(16 * 64), 256, 0, st>>>(F(L.sig_w2), g->sigma_net + 64 * ip, 16 * 64);
-  }
+  add(L4D_JOB_ADD_TRANSPOSED, L.sig_w1t, g->sigma_net, 64 * ip, 64, ip);
+  add(L4D_JOB_ADD, L.sig_w2, g->sigma_net ? g->sigma_net + 64 * ip : nullptr, 16 * 64);
   float* att[2] = {g->raydrop_net, g->intensity_net};
   for (int n = 0; n < 2; ++n) {
     if (!att[n]) continue;
-    k_add_transposed<<<nblk((size_t)64 * ap), 256, 0, st>>>(F(L.att_w1t[n]), 64, att[n], 64, ap);
-    k_add_transposed<<<nblk(64 * 64), 256, 0, st>>>(F(L.att_w2t[n]), 64, att[n] + 64 * ap, 64, 64);
-    k_add<<<1, 64, 0, st>>>(F(L.att_w3[n]), att[n] + 64 * ap + 64 * 64, 64);   // row 0 of the [16][64] output layer
+    add(L4D_JOB_ADD_TRANSPOSED, L.att_w1t[n], att[n], 64 * ap, 64, ap);
+    add(L4D_JOB_ADD_TRANSPOSED, L.att_w2t[n], att[n] + 64 * ap, 64 * 64, 64, 64);
+    add(L4D_JOB_ADD, L.att_w3[n], att[n] + 64 * ap + 64 * 64, 64);       // row 0 of the [16][64] output layer
   }
-  if (g->flow_mlp[0]) k_add_transposed<<<nblk(64 * 16), 256, 0, st>>>(F(L.flo_w0t), 64, g->flow_mlp[0], 64, 16);
-  if (g->flow_mlp[1]) k_add_transposed<<<nblk(64 * 64), 256, 0, st>>>(F(L.flo_w1t), 64, g->flow_mlp[1], 64, 64);
-  if (g->flow_mlp[2]) k_add<<<nblk(6 * 64), 256, 0, st>>>(F(L.flo_w2), g->flow_mlp[2], 6 * 64);
+  add(L4D_JOB_ADD_TRANSPOSED, L.flo_w0t, g->flow_mlp[0], 64 * 16, 64, 16);
+  add(L4D_JOB_ADD_TRANSPOSED, L.flo_w1t, g->flow_mlp[1], 64 * 64, 64, 64);
+  add(L4D_JOB_ADD, L.flo_w2, g->flow_mlp[2], 6 * 64);
+  if (nj > L4D_MAX_JOBS) return l4d_fail(L4D_EINVAL, "too many unstaging jobs");
+  if (nj == 0) return L4D_OK;
+  J.n_jobs = nj;
+  int gx = (maxn + 256 * 8 - 1) / (256 * 8);
+  ++g_launches; k_unstage_jobs<<<dim3(gx < 1 ? 1 : gx, nj), 256, 0, st>>>(J);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -943,7 +1064,7 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
     int grid;
     rc = grid_for(k_render_fwd<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
     if (rc != L4D_OK) return rc;
-    k_render_fwd<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+    ++g_launches; k_render_fwd<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
     prof_mark(st, "k_render_fwd");
     L4D_CUDA(cudaGetLastError());
     return L4D_OK;
@@ -959,7 +1080,7 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
       int grid;
       rc = grid_for(k_fwd_flow_tc, 128, smem, (uint32_t)((P + 127) / 128), grid, 4);
       if (rc != L4D_OK) return rc;
-      k_fwd_flow_tc<<<grid, 128, smem, st>>>(A);
+      ++g_launches; k_fwd_flow_tc<<<grid, 128, smem, st>>>(A);
       prof_mark(st, "k_fwd_flow_tc");
     }
     const size_t smem = 16 * L4D_NT * sizeof(float);
@@ -968,11 +1089,11 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
       const uint32_t work = rays->n_rays * A.sv.n_tiles;       // whole 128-row tiles
       rc = grid_for(k_fwd_gather<L4D_NT, true, true>, L4D_NT, smem, work, grid);
       if (rc != L4D_OK) return rc;
-      k_fwd_gather<L4D_NT, true, true><<<grid, L4D_NT, smem, st>>>(A);
+      ++g_launches; k_fwd_gather<L4D_NT, true, true><<<grid, L4D_NT, smem, st>>>(A);
     } else {
       rc = grid_for(k_fwd_gather<L4D_NT, true, false>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
       if (rc != L4D_OK) return rc;
-      k_fwd_gather<L4D_NT, true, false><<<grid, L4D_NT, smem, st>>>(A);
+      ++g_launches; k_fwd_gather<L4D_NT, true, false><<<grid, L4D_NT, smem, st>>>(A);
     }
     prof_mark(st, "k_fwd_gather");
   } else {
@@ -980,7 +1101,7 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
     int grid;
     rc = grid_for(k_fwd_gather<L4D_NT, false, false>, L4D_NT, smem, (uint32_t)((P + L4D_NT - 1) / L4D_NT), grid);
     if (rc != L4D_OK) return rc;
-    k_fwd_gather<L4D_NT, false, false><<<grid, L4D_NT, smem, st>>>(A);
+    ++g_launches; k_fwd_gather<L4D_NT, false, false><<<grid, L4D_NT, smem, st>>>(A);
     prof_mark(st, "k_fwd_gather");
   }
   if (use_tc_dense(cfg)) {
@@ -988,14 +1109,14 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
     int grid;
     rc = grid_for(k_fwd_dense_tc, 256, smem, rays->n_rays, grid);
     if (rc != L4D_OK) return rc;
-    k_fwd_dense_tc<<<grid, 256, smem, st>>>(A);
+    ++g_launches; k_fwd_dense_tc<<<grid, 256, smem, st>>>(A);
     prof_mark(st, "k_fwd_dense_tc");
   } else {
     const size_t smem = (64 * L4D_NT + 80 + 128 + 32) * sizeof(float);
     int grid;
     rc = grid_for(k_fwd_dense<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
     if (rc != L4D_OK) return rc;
-    k_fwd_dense<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+    ++g_launches; k_fwd_dense<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
     prof_mark(st, "k_fwd_dense");
   }
   L4D_CUDA(cudaGetLastError());
@@ -1033,7 +1154,7 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
       int grid;
       rc = grid_for(k_bwd_dense_tc, 256, smem, rays->n_rays, grid);
       if (rc != L4D_OK) return rc;
-      k_bwd_dense_tc<<<grid, 256, smem, st>>>(A);
+      ++g_launches; k_bwd_dense_tc<<<grid, 256, smem, st>>>(A);
       prof_mark(st, "k_bwd_dense_tc");
     } else {
       const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD + 80 + 128 + 128 + 32 + L4D_MAX_TILES) * sizeof(float);
@@ -1041,23 +1162,23 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
       rc = grid_for(k_bwd_dense<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
       if (rc != L4D_OK) return rc;
       if (grid > L4D_BWD_SCRATCH_CTAS) grid = L4D_BWD_SCRATCH_CTAS;
-      k_bwd_dense<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+      ++g_launches; k_bwd_dense<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
       prof_mark(st, "k_bwd_dense");
     }
     {
       int grid;
       rc = grid_for(k_bwd_scatter<L4D_NT>, L4D_NT, 0, tiles, grid);
       if (rc != L4D_OK) return rc;
-      k_bwd_scatter<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
+      ++g_launches; k_bwd_scatter<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
       prof_mark(st, "k_bwd_scatter");
       rc = grid_for(k_bwd_scatter_static<L4D_NT>, L4D_NT, 0, tiles, grid);
       if (rc != L4D_OK) return rc;
-      k_bwd_scatter_static<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
+      ++g_launches; k_bwd_scatter_static<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
       prof_mark(st, "k_bwd_scatter_static");
       for (int p = 0; p < 3; ++p) {
         const size_t n = cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels];
         const bool single = frame->cur.single != 0;
-        k_fold_dynamic<<<nblk(n), 256, 0, st>>>(reinterpret_cast<float4*>(A.G.hd_comb[p]),
+        ++g_launches; k_fold_dynamic<<<nblk(n), 256, 0, st>>>(reinterpret_cast<float4*>(A.G.hd_comb[p]),
                                                reinterpret_cast<float4*>(A.G.hd[p][frame->cur.slice_lo]),
                                                single ? nullptr : reinterpret_cast<float4*>(A.G.hd[p][frame->cur.slice_hi]), n,
                                                single ? 1.0f : frame->cur.w_lo, frame->cur.w_hi);
@@ -1070,21 +1191,21 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
         int grid;
         rc = grid_for(k_bwd_flow_tc, 128, smem, tiles, grid, 2);     // 92 KB + 256 TMEM columns: two per SM
         if (rc != L4D_OK) return rc;
-        k_bwd_flow_tc<<<grid, 128, smem, st>>>(A);
+        ++g_launches; k_bwd_flow_tc<<<grid, 128, smem, st>>>(A);
         prof_mark(st, "k_bwd_flow_tc");
         rc = grid_for(k_bwd_flowgrid<L4D_NT>, L4D_NT, 0, tiles, grid);
         if (rc != L4D_OK) return rc;
-        k_bwd_flowgrid<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
+        ++g_launches; k_bwd_flowgrid<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
         const size_t n = cfg->flow.offset[cfg->flow.n_levels];
         const float* fb = frame->flow_basis;
-        k_fold_flow<<<nblk(n), 256, 0, st>>>(reinterpret_cast<float2*>(A.G.hf_comb), reinterpret_cast<float4*>(A.G.hf), n, fb[0], fb[1], fb[2], fb[3]);
+        ++g_launches; k_fold_flow<<<nblk(n), 256, 0, st>>>(reinterpret_cast<float2*>(A.G.hf_comb), reinterpret_cast<float4*>(A.G.hf), n, fb[0], fb[1], fb[2], fb[3]);
         prof_mark(st, "k_bwd_flowgrid");
       } else {
         const size_t smem = (64 * L4D_NT + 2 * L4D_NT * L4D_TILE_LD) * sizeof(float);
         int grid;
         rc = grid_for(k_bwd_flow<L4D_NT>, L4D_NT, smem, tiles, grid);
         if (rc != L4D_OK) return rc;
-        k_bwd_flow<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+        ++g_launches; k_bwd_flow<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
         prof_mark(st, "k_bwd_flow");
       }
     }
@@ -1106,7 +1227,7 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
   rc = grid_for(k_render_bwd<L4D_NT>, L4D_NT, smem, rays->n_rays, grid);
   if (rc != L4D_OK) return rc;
   if (grid > L4D_BWD_SCRATCH_CTAS) grid = L4D_BWD_SCRATCH_CTAS;
-  k_render_bwd<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
+  ++g_launches; k_render_bwd<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
   prof_mark(st, "k_render_bwd");
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
@@ -1126,7 +1247,7 @@ extern "C" int l4d_flow_forward(const L4DConfig* cfg, const void* staged, const 
   int grid;
   rc = grid_for(k_flow_fwd<L4D_NT>, L4D_NT, smem, (n + L4D_NT - 1) / L4D_NT, grid);
   if (rc != L4D_OK) return rc;
-  k_flow_fwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  ++g_launches; k_flow_fwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -1157,7 +1278,7 @@ extern "C" int l4d_flow_backward(const L4DConfig* cfg, const void* staged, const
   int grid;
   rc = grid_for(k_flow_bwd<L4D_NT>, L4D_NT, smem, (n + L4D_NT - 1) / L4D_NT, grid);
   if (rc != L4D_OK) return rc;
-  k_flow_bwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  ++g_launches; k_flow_bwd<L4D_NT><<<grid, L4D_NT, smem, (cudaStream_t)stream>>>(A);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -1172,7 +1293,7 @@ extern "C" int l4d_hash_indices(const L4DConfig* cfg, uint32_t grid_id, uint32_t
   if (n == 0) return L4D_OK;
   DevGrid d;
   fill_grid(d, g);
-  k_hash_indices<<<nblk(n), 256, 0, (cudaStream_t)stream>>>(d, (int)g.n_dims, (int)level, x, n, idx, w);
+  ++g_launches; k_hash_indices<<<nblk(n), 256, 0, (cudaStream_t)stream>>>(d, (int)g.n_dims, (int)level, x, n, idx, w);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -1189,7 +1310,7 @@ extern "C" int l4d_density_forward(const L4DConfig* cfg, const void* staged, con
   A.F = *frame; A.x = x; A.n = n; A.sigma = sigma; A.geo = geo; A.features = features; A.flow = flow;
   const size_t smem = 64 * L4D_NT * sizeof(float);
   L4D_CUDA(cudaFuncSetAttribute(k_density<L4D_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_density<L4D_NT><<<nblk(n, L4D_NT), L4D_NT, smem, (cudaStream_t)stream>>>(A);
+  ++g_launches; k_density<L4D_NT><<<nblk(n, L4D_NT), L4D_NT, smem, (cudaStream_t)stream>>>(A);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -1207,7 +1328,7 @@ extern "C" int l4d_attribute_forward(const L4DConfig* cfg, const void* staged, c
   constexpr int NT = 64;
   const size_t smem = (size_t)(64 + 81 + 129) * NT * sizeof(float);
   L4D_CUDA(cudaFuncSetAttribute(k_attribute<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_attribute<NT><<<nblk(n, NT), NT, smem, (cudaStream_t)stream>>>(A);
+  ++g_launches; k_attribute<NT><<<nblk(n, NT), NT, smem, (cudaStream_t)stream>>>(A);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -1218,7 +1339,7 @@ extern "C" int l4d_tc_selftest(const void* A, const void* B, float* Cout, uint32
   if (N < 16 || N > 256 || N % 16 || K < 16 || K % 16 || K > 512) return l4d_fail(L4D_EINVAL, "need N%16==0 in [16,256], K%16==0 in [16,512]");
   const size_t smem = (size_t)(K / 8) * (128 + N) * 16 + 1024;
   L4D_CUDA(cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_tc_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(B),
+  ++g_launches; k_tc_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(B),
                                                         Cout, (int)N, (int)K);
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
@@ -1232,7 +1353,7 @@ extern "C" int l4d_tc_selftest2(const void* A, const void* B, float* Cout, uint3
     return l4d_fail(L4D_EINVAL, "need M in {64,128}, N%8==0 (N%16 for M=128) <= 256, K%16==0 <= 256");
   const size_t smem = (size_t)(((M * K * 2 + 1023) & ~1023u) + N * K * 2 + 2048);
   L4D_CUDA(cudaFuncSetAttribute(k_tc_selftest2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_tc_selftest2<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned char*>(A),
+  ++g_launches; k_tc_selftest2<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned char*>(A),
                                                          reinterpret_cast<const unsigned char*>(B), Cout, (int)M, (int)N, (int)K,
                                                          (int)a_mn, (int)b_mn);
   L4D_CUDA(cudaGetLastError());

@@ -106,9 +106,23 @@ class _FlowField(nn.Module):
 
 
 # =============================================================================
-# engine: staging, pointer tables, launches
+# engine: flat arenas, staging, pointer tables, launches
 # =============================================================================
+ARENA_ALIGN = 1024          # floats; = L4D_ADAM_CHUNK of include/lidar4d_b200.h
+
+
 class _Engine:
+    """Owns what the kernels need besides the caller's tensors:
+
+    * ONE flat fp32 parameter arena - every hot-path parameter's ``.data`` is a view into it (state_dict keys, shapes
+      and ``load_state_dict`` are unchanged; after ``model.to(device)`` the views are rebuilt lazily) - and ONE flat
+      fp32 gradient arena that every ``.grad`` views: the backward kernels accumulate straight into it (no per-launch
+      allocation, no autograd accumulation pass), ``RayShardedDP`` all-reduces it in place, ``lidar4d_b200.optim.Adam``
+      updates both arenas in one launch;
+    * the staged working set (fp16 tables, channels-last planes, MLP operand copies), refreshed when a master changed;
+    * the persistent gradient work buffer (zero between launches: the fold kernels clear what they consume).
+    """
+
     def __init__(self, owner: "LiDAR4D"):
         self.owner = owner
         self.cfg = owner.cfg
@@ -120,7 +134,17 @@ class _Engine:
         self.lib = None
         self.staged = None
         self._stamp = None
-        self.n_launches = 0        # kernels of this library launched so far (bench "gpu_launches")
+        self._staged_grad_mode = None
+        self._chk = None
+        self.stage_gen = 0         # bumped by every re-staging; forward records it, backward checks it
+        self.static_params = False # True: skip the content check of no-grad calls (tight inference loops)
+        self.flat_p = None
+        self.flat_g = None
+        self.grad_work = None
+        self.offsets = None        # name -> (offset, numel) in floats
+        self.total = 0
+        self._gtab = None
+        self._launch_base = 0
         self.timing = None         # {'fwd': [(ev0, ev1)], 'bwd': [...]}: CUDA events around the fused kernels
 
     def set_mlp_fp16(self, on: bool):
@@ -160,43 +184,161 @@ class _Engine:
         self.timing[kind].append(ev)
         return ev
 
+    @property
+    def n_launches(self) -> int:
+        """Kernels this library launched (counted inside the library, l4d_launch_count)."""
+        return int(self._lib().l4d_launch_count())
+
+    # ---- flat arenas ------------------------------------------------------------
+    def _layout(self, ts):
+        if self.offsets is None:
+            o, offs = 0, {}
+            for n in self.names:
+                offs[n] = (o, ts[n].numel())
+                o += (ts[n].numel() + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+            self.offsets, self.total = offs, o
+        return self.offsets
+
+    def ensure_flat(self, ts=None) -> bool:
+        """Make every hot-path parameter a view into the flat arena.  Returns True if the arena was (re)built."""
+        ts = ts or self.tensors()
+        offs = self._layout(ts)
+        dev = self.device()
+        if self.flat_p is not None and self.flat_p.device == dev:
+            base = self.flat_p.data_ptr()
+            if all(t.data_ptr() == base + 4 * offs[n][0] for n, t in ts.items()):
+                return False
+        for n, t in ts.items():
+            if t.dtype != torch.float32 or t.device != dev:
+                raise RuntimeError(f"parameter {n} must be fp32 on {dev} (got {t.dtype} on {t.device})")
+        flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for n, t in ts.items():
+                o, k = offs[n]
+                v = flat[o:o + k].view(t.shape)
+                v.copy_(t)
+                t.data = v
+        self.flat_p, self.flat_g, self._gtab, self._stamp = flat, None, None, None
+        return True
+
+    def attach_grads(self):
+        """Point every trainable parameter's .grad at its slice of the flat gradient arena (zeroing slices whose
+        .grad was None / copying foreign gradients in) and return the pointer table the kernels accumulate into."""
+        ts = self.tensors()
+        self.ensure_flat(ts)
+        fresh = False
+        if self.flat_g is None or self.flat_g.device != self.flat_p.device:
+            self.flat_g = torch.zeros(self.total, dtype=torch.float32, device=self.flat_p.device)
+            self._gtab, fresh = None, True
+        base = self.flat_g.data_ptr()
+        stale, n_train = [], 0
+        for n, t in ts.items():
+            if not t.requires_grad:
+                continue
+            n_train += 1
+            g = t.grad
+            if g is None or g.data_ptr() != base + 4 * self.offsets[n][0] or g.dtype != torch.float32 or g.shape != t.shape:
+                stale.append((n, t, g))
+        if stale:
+            all_none = len(stale) == n_train and all(g is None for _, _, g in stale)
+            with torch.no_grad():
+                if all_none and not fresh:
+                    self.flat_g.zero_()                     # the usual case: optimizer.zero_grad(set_to_none=True)
+                for n, t, g in stale:
+                    o, k = self.offsets[n]
+                    v = self.flat_g[o:o + k].view(t.shape)
+                    if not all_none:
+                        if g is None:
+                            v.zero_()
+                        else:
+                            v.copy_(g)
+                    t.grad = v
+        if self._gtab is None:
+            self._gtab = _capi.L4DMasterGrads()
+            _capi.fill_pointer_table(self._gtab, self.cfg, lambda n: base + 4 * self.offsets[n][0])
+        return self._gtab
+
+    def work(self):
+        """Persistent zero-initialised gradient work buffer (plane / MLP grads in working layout, slice-independent
+        hash accumulators).  Every kernel that consumes a region clears it again."""
+        if self.grad_work is None or self.grad_work.device != self.device():
+            n = self._lib().l4d_grad_work_bytes(C.byref(self.ccfg))
+            self.grad_work = torch.zeros(n, dtype=torch.uint8, device=self.device())
+        return self.grad_work
+
+    def reset_work(self):
+        """Call after an exception inside a backward left the work buffer half-consumed."""
+        if self.grad_work is not None:
+            self.grad_work.zero_()
+
+    # ---- staging ----------------------------------------------------------------
+    def invalidate_staged(self):
+        """Force the next call to refresh the kernels' working set.  Needed after in-place writes that bypass
+        autograd's version counter in GRAD mode (``p.data.copy_()``); no-grad calls check the content themselves."""
+        self._stamp = None
+
+    def _checksum(self) -> int:
+        return int(self.flat_p.view(torch.int32).sum(dtype=torch.int64))
+
+    def master_table(self):
+        tab = _capi.L4DMasterParams()
+        base = self.flat_p.data_ptr()
+        _capi.fill_pointer_table(tab, self.cfg, lambda n: base + 4 * self.offsets[n][0])
+        return tab
+
     def ensure_staged(self):
-        """Refresh the fp16 / channels-last / transposed working set when any
-        master parameter changed (optimizer.step bumps tensor._version)."""
+        """Refresh the fp16 / channels-last / transposed working set when a master parameter changed.
+        Change detection: autograd version counters (optimizer.step, load_state_dict) in grad mode; in no-grad mode
+        additionally the CONTENT (one reduction + one 8-byte read), because torch_ema's copy_to()/restore()
+        (runner.py:565-567,680,820) write through ``.data`` and leave the counters alone; and always when the grad mode
+        flipped since the last staging (eval -> train after ema.restore())."""
         lib = self._lib()
         ts = self.tensors()
-        stamp = tuple((t.data_ptr(), t._version) for t in ts.values())
-        if self.staged is not None and stamp == self._stamp and self.staged.device == self.device():
+        reflat = self.ensure_flat(ts)
+        grad_mode = torch.is_grad_enabled()
+        stamp = tuple(t._version for t in ts.values())
+        need = (self.staged is None or reflat or stamp != self._stamp or self.staged.device != self.device()
+                or grad_mode != self._staged_grad_mode)
+        chk = None
+        if not need and not grad_mode and not self.static_params:
+            chk = self._checksum()
+            need = chk != self._chk
+        if not need:
             return
-        for n, t in ts.items():
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                raise RuntimeError(f"parameter {n} must be contiguous fp32")
         nbytes = lib.l4d_staged_bytes(C.byref(self.ccfg))
         if nbytes == 0:
             raise RuntimeError("unsupported configuration: " + lib.l4d_last_error().decode())
-        if self.staged is None or self.staged.device != self.device():
-            self.staged = torch.empty(nbytes, dtype=torch.uint8, device=self.device())
-        tab = _capi.L4DMasterParams()
-        _capi.fill_pointer_table(tab, self.cfg, lambda n: ts[n].data_ptr())
+        if self.staged is None or self.staged.device != self.device() or self.staged.numel() != nbytes:
+            self.staged = torch.zeros(nbytes, dtype=torch.uint8, device=self.device())
+        self.stage(_capi.STAGE_TABLES | _capi.STAGE_SMALL)
+        self._stamp, self._staged_grad_mode = stamp, grad_mode
+        if not grad_mode and not self.static_params:
+            self._chk = chk if chk is not None else self._checksum()
+
+    def stage(self, what: int):
+        lib = self._lib()
+        tab = self.master_table()
         with torch.cuda.device(self.device()):
-            rc = lib.l4d_stage_params(C.byref(self.ccfg), C.byref(tab), self.staged.data_ptr(), nbytes, self.stream())
-        _capi.check(lib, rc, "l4d_stage_params")
-        self.n_launches += 2 + 3 * self.cfg.time_resolution + 6 * self.cfg.n_levels_plane + 16 + 12 + (1 if self.mlp_fp16 else 0)
-        self._stamp = stamp
+            rc = lib.l4d_stage_params_ex(C.byref(self.ccfg), C.byref(tab), self.staged.data_ptr(), self.staged.numel(),
+                                         what, self.stream())
+        _capi.check(lib, rc, "l4d_stage_params_ex")
+        self.stage_gen += 1
 
-    # ---- gradient arena -------------------------------------------------------
-    def new_grad_arena(self):
-        ts = self.tensors()
-        sizes = [ts[n].numel() for n in self.names]
-        offs = np.concatenate([[0], np.cumsum([(s + 63) // 64 * 64 for s in sizes])])
-        flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=self.device())
-        views = {n: flat[int(offs[i]):int(offs[i]) + sizes[i]].view_as(ts[n]) for i, n in enumerate(self.names)}
-        return flat, views
+    def params_updated_by_optimizer(self, tables_staged: bool):
+        """lidar4d_b200.optim.Adam wrote the parameter arena (and, fused, the fp16 tables): finish the refresh."""
+        if self.staged is None:
+            self._stamp = None
+            return
+        self.stage(_capi.STAGE_SMALL if tables_staged else (_capi.STAGE_TABLES | _capi.STAGE_SMALL))
+        self._chk = None
+        self._staged_grad_mode = True
 
-    def grad_table(self, views):
-        tab = _capi.L4DMasterGrads()
-        _capi.fill_pointer_table(tab, self.cfg, lambda n: views[n].data_ptr())
-        return tab
+    def check_generation(self, ctx_gen: int, what: str):
+        if ctx_gen != self.stage_gen:
+            raise RuntimeError(
+                f"{what}: the model's parameters (or its MLP precision mode) changed between this forward and its "
+                "backward; the kernels' working set was re-staged in between.  Run backward before optimizer.step() / "
+                "set_mlp_fp16() / load_state_dict().")
 
     def frame(self, time) -> _capi.L4DFrame:
         if torch.is_tensor(time):
@@ -205,8 +347,10 @@ class _Engine:
 
 
 class _RenderFn(torch.autograd.Function):
-    """Fused render forward / backward.  Parameters are passed as inputs so that
-    autograd routes their gradients; the kernels read the staged working set."""
+    """Fused render forward / backward.  Parameters are passed as inputs so that autograd schedules the backward;
+    their gradients are accumulated by the kernels straight into the flat gradient arena that every ``.grad`` views
+    (model.grad_mode == "arena", the default), or returned to autograd as fresh tensors ("autograd": works with
+    torch.autograd.grad, costs one arena allocation + one accumulation pass per backward)."""
 
     @staticmethod
     def forward(ctx, eng: _Engine, rays_o, rays_d, frame, S, perturb, seed, ray_offset, want_weights, train, *params):
@@ -238,12 +382,11 @@ class _RenderFn(torch.autograd.Function):
                 saved.data_ptr() if saved is not None else None, nsaved, eng.stream())
             if ev: ev[1].record()
         _capi.check(lib, rc, "l4d_render_forward")
-        eng.n_launches += 1 if fused else (3 if eng.mlp_fp16 else 2)
         ctx.eng, ctx.frame, ctx.rays_args = eng, frame, (N, S, int(bool(perturb)), int(seed), int(ray_offset))
         ctx.saved, ctx.nsaved = (saved, nsaved) if train else (None, 0)
         ctx.fused = fused
         ctx.rays_o, ctx.rays_d = rays_o, rays_d
-        ctx.staged = eng.staged
+        ctx.stage_gen = eng.stage_gen
         ctx.want_weights = want_weights
         if want_weights:
             ctx.mark_non_differentiable(zvals)
@@ -256,6 +399,7 @@ class _RenderFn(torch.autograd.Function):
         lib = eng._lib()
         if ctx.saved is None:
             raise RuntimeError("render was run without saving activations (no_grad / eval)")
+        eng.check_generation(ctx.stage_gen, "render backward")
         N, S, perturb, seed, ray_offset = ctx.rays_args
         dev = ctx.rays_o.device
         g_weights = rest[0] if (ctx.want_weights and len(rest) > 0) else None
@@ -263,10 +407,9 @@ class _RenderFn(torch.autograd.Function):
         g_depth, g_image = z(g_depth, (N,)), z(g_image, (N, 2))
         g_wsum = None if g_wsum is None else g_wsum.contiguous().float()
         g_weights = None if g_weights is None else g_weights.contiguous().float()
-        flat, views = eng.new_grad_arena()
-        tab = eng.grad_table(views)
-        nwork = lib.l4d_grad_work_bytes(C.byref(eng.ccfg))
-        work = torch.zeros(nwork, dtype=torch.uint8, device=dev)
+        arena = eng.owner.grad_mode == "arena"
+        tab, views = (eng.attach_grads(), None) if arena else _scratch_grads(eng)
+        work = eng.work()
         rays = _capi.L4DRays()
         rays.rays_o, rays.rays_d = ctx.rays_o.data_ptr(), ctx.rays_d.data_ptr()
         rays.n_rays, rays.n_steps, rays.perturb, rays.seed, rays.ray_offset = N, S, perturb, seed, ray_offset
@@ -275,19 +418,30 @@ class _RenderFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             if ev: ev[0].record()
             rc = lib.l4d_render_backward(
-                C.byref(eng.ccfg), ctx.staged.data_ptr(), C.byref(ctx.frame), C.byref(rays),
+                C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(ctx.frame), C.byref(rays),
                 ctx.saved.data_ptr(), ctx.nsaved, g_depth.data_ptr(), g_image.data_ptr(),
                 g_wsum.data_ptr() if g_wsum is not None else None,
                 g_weights.data_ptr() if g_weights is not None else None,
-                C.byref(tab), work.data_ptr(), nwork, eng.stream())
+                C.byref(tab), work.data_ptr(), work.numel(), eng.stream())
             if ev: ev[1].record()
             _capi.check(lib, rc, "l4d_render_backward")
-            rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), nwork, C.byref(tab), eng.stream())
+            rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), work.numel(), C.byref(tab), eng.stream())
             _capi.check(lib, rc, "l4d_unstage_grads")
-        eng.n_launches += (1 if ctx.fused else (9 if eng.mlp_fp16 else 7)) + 6 * eng.cfg.n_levels_plane + 11
-        eng.owner._last_grad_arena = flat
         ctx.saved = None
+        if arena:
+            return (None,) * (10 + len(eng.names))
         return (None,) * 10 + tuple(views[n] for n in eng.names)
+
+
+def _scratch_grads(eng: _Engine):
+    """grad_mode == "autograd": a fresh zeroed arena whose views are handed to autograd."""
+    ts = eng.tensors()
+    eng.ensure_flat(ts)
+    flat = torch.zeros(eng.total, dtype=torch.float32, device=eng.device())
+    views = {n: flat[o:o + k].view(ts[n].shape) for n, (o, k) in eng.offsets.items()}
+    tab = _capi.L4DMasterGrads()
+    _capi.fill_pointer_table(tab, eng.cfg, lambda n: views[n].data_ptr())
+    return tab, views
 
 
 class _FlowFn(torch.autograd.Function):
@@ -301,8 +455,7 @@ class _FlowFn(torch.autograd.Function):
             rc = lib.l4d_flow_forward(C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(frame), x.data_ptr(), n,
                                       flow.data_ptr(), saved.data_ptr() if train else None, eng.stream())
         _capi.check(lib, rc, "l4d_flow_forward")
-        eng.n_launches += 1
-        ctx.eng, ctx.frame, ctx.x, ctx.saved, ctx.staged = eng, frame, x, saved, eng.staged
+        ctx.eng, ctx.frame, ctx.x, ctx.saved, ctx.stage_gen = eng, frame, x, saved, eng.stage_gen
         return flow
 
     @staticmethod
@@ -311,21 +464,22 @@ class _FlowFn(torch.autograd.Function):
         lib = eng._lib()
         if ctx.saved is None:
             raise RuntimeError("flow was run without saving activations")
+        eng.check_generation(ctx.stage_gen, "flow backward")
         x = ctx.x
         n = x.shape[0]
         g_flow = g_flow.contiguous().float()
-        flat, views = eng.new_grad_arena()
-        tab = eng.grad_table(views)
-        nwork = lib.l4d_grad_work_bytes(C.byref(eng.ccfg))
-        work = torch.zeros(nwork, dtype=torch.uint8, device=x.device)
+        arena = eng.owner.grad_mode == "arena"
+        tab, views = (eng.attach_grads(), None) if arena else _scratch_grads(eng)
+        work = eng.work()
         with torch.cuda.device(x.device):
-            rc = lib.l4d_flow_backward(C.byref(eng.ccfg), ctx.staged.data_ptr(), C.byref(ctx.frame), x.data_ptr(), n,
-                                       ctx.saved.data_ptr(), g_flow.data_ptr(), C.byref(tab), work.data_ptr(), nwork,
+            rc = lib.l4d_flow_backward(C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(ctx.frame), x.data_ptr(), n,
+                                       ctx.saved.data_ptr(), g_flow.data_ptr(), C.byref(tab), work.data_ptr(), work.numel(),
                                        eng.stream())
             _capi.check(lib, rc, "l4d_flow_backward")
-            rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), nwork, C.byref(tab), eng.stream())
+            rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), work.numel(), C.byref(tab), eng.stream())
             _capi.check(lib, rc, "l4d_unstage_grads")
-        eng.n_launches += 1 + 6 * eng.cfg.n_levels_plane + 11
+        if arena:
+            return (None,) * (4 + len(eng.names))
         flow_names = {"flow_net.grid_enc.params", "flow_net.mlp.0.weight", "flow_net.mlp.2.weight", "flow_net.mlp.4.weight"}
         return (None,) * 4 + tuple(views[n] if n in flow_names else None for n in eng.names)
 
@@ -414,9 +568,11 @@ class LiDAR4D(LiDAR_Renderer):
         # "split": gather / dense / scatter kernels exchanging SoA planes (default, faster);
         # "fused": the single-kernel forward and backward (csrc/l4d_kernels.cu)
         self.pipeline = "split"
+        # "arena": the backward kernels accumulate into the flat gradient arena that every .grad views (default);
+        # "autograd": gradients are returned to autograd as tensors (torch.autograd.grad, hooks), slower
+        self.grad_mode = "arena"
         self.jitter_seed = 0
         self._jitter_calls = 0
-        self._last_grad_arena = None
         self._engine = _Engine(self)
 
     # ---- precision / pipeline switches ------------------------------------------------------
@@ -426,6 +582,20 @@ class LiDAR4D(LiDAR_Renderer):
         tcgen05 tensor cores with hi/lo-split fp16 activations (fp32-class accuracy) -- the default.
         False: fp32 weights on the fp32-FMA kernels (bit-for-bit the fp32 oracle's arithmetic, ~2x slower)."""
         self._engine.set_mlp_fp16(on)
+        return self
+
+    def invalidate_staged(self):
+        """Refresh the kernels' working set at the next call.  Only needed after in-place parameter writes that bypass
+        autograd's version counter WHILE GRADIENTS ARE ENABLED (``p.data.copy_(...)``); optimizer steps,
+        ``load_state_dict`` and anything done before a ``torch.no_grad()`` render (torch_ema ``copy_to``/``restore``
+        around evaluation, runner.py:565-567,680) are detected automatically."""
+        self._engine.invalidate_staged()
+        return self
+
+    def static_params(self, on: bool = True):
+        """Promise that parameters do not change between no-grad calls (skips the per-call content check, one
+        reduction + an 8-byte device->host read): for tight inference loops such as a trajectory render."""
+        self._engine.static_params = bool(on)
         return self
 
     # ---- nn.Module plumbing -----------------------------------------------------------------
@@ -491,7 +661,6 @@ class LiDAR4D(LiDAR_Renderer):
                                          feats.data_ptr() if return_features else None,
                                          flow.data_ptr() if return_features else None, eng.stream())
         _capi.check(lib, rc, "l4d_density_forward")
-        eng.n_launches += 1
         out = {"sigma": sigma, "geo_feat": geo}
         if return_features:
             out.update(features=feats, flow=flow)
@@ -515,7 +684,6 @@ class LiDAR4D(LiDAR_Renderer):
             rc = lib.l4d_attribute_forward(C.byref(eng.ccfg), eng.staged.data_ptr(), d.data_ptr(), geo.data_ptr(),
                                            m8.data_ptr() if m8 is not None else None, n, out.data_ptr(), eng.stream())
         _capi.check(lib, rc, "l4d_attribute_forward")
-        eng.n_launches += 1
         return out
 
     @torch.no_grad()
@@ -532,7 +700,6 @@ class LiDAR4D(LiDAR_Renderer):
             rc = lib.l4d_hash_indices(C.byref(eng.ccfg), grid_id, level, x.data_ptr(), n, idx.data_ptr(), w.data_ptr(),
                                       eng.stream())
         _capi.check(lib, rc, "l4d_hash_indices")
-        eng.n_launches += 1
         return idx, w
 
     # ---- optimizer utils (lidar4d.py:226-237) ----------------------------------------------------

@@ -190,12 +190,13 @@ def jitter_uniform(seed: int, ray_index: np.ndarray, n_steps: int) -> np.ndarray
 
 
 def sample_lin(n_steps: int) -> np.ndarray:
-    """torch.linspace(0,1,S) with the CUDA kernel's formula (the reference runs
-    on CUDA): step*j below the midpoint, 1-step*(S-1-j) above, fp32."""
+    """torch.linspace(0,1,S) exactly as the CUDA kernel computes it (the reference renders on the GPU,
+    renderer.py:77): step*j below the midpoint, fma(-step, S-1-j, 1) - ONE rounding - above it.  Pinned against the
+    real thing: tests/golden/cuda_linspace.npz was dumped from torch.linspace(device="cuda") on a B200."""
     step = np.float32(1.0) / np.float32(n_steps - 1) if n_steps > 1 else np.float32(0)
     j = np.arange(n_steps)
     lo = (step * j.astype(np.float32)).astype(np.float32)
-    hi = (np.float32(1.0) - (step * (n_steps - 1 - j).astype(np.float32)).astype(np.float32)).astype(np.float32)
+    hi = (1.0 - np.float64(step) * (n_steps - 1 - j).astype(np.float64)).astype(np.float32)   # exact product, one rounding
     return np.where(j < n_steps // 2, lo, hi).astype(np.float32)
 
 
@@ -432,8 +433,10 @@ class OracleLiDAR4D(nn.Module):
     # -- LiDAR_Renderer.run ----------------------------------------------------
     def render(self, rays_o: torch.Tensor, rays_d: torch.Tensor, time, num_steps: int = 768,
                perturb: bool = False, seed: int = 0, ray_offset: int = 0, lin: Optional[np.ndarray] = None,
-               return_stages: bool = False):
-        """model/renderer.py:44-140 on [N,3] rays."""
+               return_stages: bool = False, mask_override: Optional[torch.Tensor] = None):
+        """model/renderer.py:44-140 on [N,3] rays.  mask_override [N,S] bool replaces the (non-differentiable)
+        `weights > 1e-4` attribute mask: parity tests align it with the implementation under test when a weight sits
+        within fp32 rounding of the threshold, where either decision is a correct evaluation of the reference."""
         c = self.cfg
         rays_o = rays_o.reshape(-1, 3).float()
         rays_d = rays_d.reshape(-1, 3).float()
@@ -459,6 +462,8 @@ class OracleLiDAR4D(nn.Module):
         shifted = torch.cat([torch.ones_like(alphas[:, :1]), 1 - alphas + 1e-15], -1)
         weights = alphas * torch.cumprod(shifted, -1)[:, :-1]                   # :104
         mask = weights > 1e-4                                                   # :110
+        if mask_override is not None:
+            mask = mask_override.to(mask.device).view_as(mask)
         dirs = rays_d.view(-1, 1, 3).expand(N, num_steps, 3).reshape(-1, 3)
         attr = self.attribute(dirs, dens["geo_feat"], mask.reshape(-1)).view(N, num_steps, -1)
         wsum = weights.sum(-1)                                                  # :121
@@ -499,6 +504,29 @@ def snap_mlp_weights_fp16(model: OracleLiDAR4D) -> OracleLiDAR4D:
         for k in MLP_PARAM_NAMES:
             v = model.P[k]
             v.copy_(v.to(torch.float16).to(v.dtype))
+    return model
+
+
+def band_limit_tables(model: OracleLiDAR4D) -> OracleLiDAR4D:
+    """Scale hash level l by resolution_0 / resolution_l ("trained-like" tables: the amplitude of a level falls with its
+    cell size, so every level contributes the same slope).  With the white-noise tables of randomize_parameters one ulp
+    (6e-8) of a warped coordinate x + flow moves a 32769-cell level by 2e-3 cells = a 1e-3 feature change: two correct
+    fp32 implementations then differ by ~5e-5 in the weights and disagree on ReLU / texel decisions of individual
+    samples, which shows up as per-entry differences of sparse table gradients (measured on the B200:
+    profiles/r02_parity_*).  Band-limited tables keep that amplification at 1 and gradients comparable entry by entry."""
+    with torch.no_grad():
+        for k, v in model.P.items():
+            if "hash_static" in k:
+                geo = model.g_static
+            elif "grid_enc" in k:
+                geo = model.g_flow
+            elif "hash_dynamic" in k:
+                geo = model.g_dynamic[int(k.split("/")[2])]
+            else:
+                continue
+            t = v.view(-1, geo.n_features)
+            for l in range(geo.n_levels):
+                t[int(geo.offset[l]):int(geo.offset[l + 1])] *= float(geo.resolution[0]) / float(geo.resolution[l])
     return model
 
 

@@ -72,6 +72,7 @@ def to_np(d):
 
 
 FULL = dict(num_frames=51, near_lidar=0.0105, far_lidar=0.851)     # everything else = the reference's defaults
+MASK_MARGIN = 5e-7                                                  # min |w - 1e-4| of a full-size case (see run_case)
 BIG = 70000                                                         # gradients above this size are stored as samples
 
 
@@ -90,15 +91,34 @@ def build_reference_full(levels):
     return l4d.LiDAR4D(n_levels_hash=levels, **FULL)
 
 
-def run_case(name, time, n_rays_hw, num_steps, perturb, seed, levels=None):
+def run_case(name, time, n_rays_hw, num_steps, perturb, seed, levels=None, smooth=False):
     """levels=None: the small-table configuration; levels=8/16: the full-size (benchmarked) configuration with
     every MLP master weight snapped to an fp16-representable value (O.snap_mlp_weights_fp16), so that the
     reference's fp32 arithmetic on the shim is at the same time the function the tensor-core kernels evaluate
     with their fp16 working copies - one fixture pins both CUDA modes."""
     full = levels is not None
+    H, W = n_rays_hw
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, 3] = [0.1, -0.05, 0.02]
+    ro, rd = lidar_rays(pose, H, W, fov_up=2.0, fov=26.9)
     if full:
-        orc = O.build_seeded(full_config(levels), seed, flow_last_std=0.02)
-        O.snap_mlp_weights_fp16(orc)
+        # In this regime (white-noise tables, sigma ~ 1) ~1 % of the 12k weights lie below the 1e-4 attribute mask
+        # threshold (renderer.py:110) and a handful within 1e-6 of it, where fp32 rounding decides the (non-
+        # differentiable) mask.  Take the first seed whose closest weight keeps MASK_MARGIN from the threshold, so that
+        # any correct fp32 implementation takes the same decisions as the reference run recorded here.
+        for seed in range(seed, seed + 400):
+            orc = O.build_seeded(full_config(levels), seed, flow_last_std=0.02)
+            O.snap_mlp_weights_fp16(orc)
+            if smooth:
+                O.band_limit_tables(orc)
+            with torch.no_grad():
+                w = orc.render(torch.from_numpy(ro), torch.from_numpy(rd), time, num_steps=num_steps, perturb=perturb, seed=seed)["weights"]
+            margin = float((w - 1e-4).abs().min())
+            if margin >= MASK_MARGIN:
+                break
+        else:
+            raise RuntimeError("no seed with the required mask margin")
+        print(f"[{name}] seed {seed}: mask margin {margin:.2e}, mask fraction {float((w > 1e-4).float().mean()):.3f}")
         ref = build_reference_full(levels)
     else:
         orc = oracle_for(SMALL, seed)
@@ -108,10 +128,6 @@ def run_case(name, time, n_rays_hw, num_steps, perturb, seed, levels=None):
     assert all(k.startswith("unet") for k in missing.missing_keys), missing
     assert not missing.unexpected_keys, missing
 
-    H, W = n_rays_hw
-    pose = np.eye(4, dtype=np.float32)
-    pose[:3, 3] = [0.1, -0.05, 0.02]
-    ro, rd = lidar_rays(pose, H, W, fov_up=2.0, fov=26.9)
     rays_o = torch.from_numpy(ro)[None]
     rays_d = torch.from_numpy(rd)[None]
     t = torch.tensor([[time]], dtype=torch.float32)
@@ -196,6 +212,8 @@ def run_case(name, time, n_rays_hw, num_steps, perturb, seed, levels=None):
         fx["grad:" + k] = g.numpy().astype(np.float32)
     if full:
         fx["levels"] = levels
+        fx["mask_margin"] = np.float64(margin)
+        fx["smooth"] = int(smooth)
         for k, g in ref_grads.items():
             if g.numel() <= BIG:
                 continue
@@ -263,6 +281,8 @@ if __name__ == "__main__":
     run_case("ref_small_last", time=1.0, n_rays_hw=(3, 10), num_steps=40, perturb=True, seed=5)
     # the benchmarked configuration (BASELINE.json configs[1]): default tables, S=768, jitter on
     run_case("ref_full_L16_interior", time=7 / 50, n_rays_hw=(2, 8), num_steps=768, perturb=True, seed=21, levels=16)
-    run_case("ref_full_L8_interior", time=0.4, n_rays_hw=(2, 8), num_steps=768, perturb=True, seed=22, levels=8)
+    # the same with band-limited ("trained-like") tables: the gradient-parity cases (see O.band_limit_tables)
+    run_case("ref_full_L16_smooth", time=7 / 50, n_rays_hw=(2, 8), num_steps=768, perturb=True, seed=21, levels=16, smooth=True)
+    run_case("ref_full_L8_smooth", time=0.4, n_rays_hw=(2, 8), num_steps=768, perturb=True, seed=22, levels=8, smooth=True)
     run_case("ref_full_L16_first", time=0.0, n_rays_hw=(2, 6), num_steps=768, perturb=False, seed=23, levels=16)
     run_case("ref_full_L8_last", time=1.0, n_rays_hw=(2, 6), num_steps=768, perturb=True, seed=24, levels=8)

@@ -88,22 +88,22 @@ def full_config(levels: int) -> FieldConfig:
     return FieldConfig(n_levels_hash=levels, **FULL)
 
 
-def full_oracle(levels: int, seed: int):
+def full_oracle(levels: int, seed: int, smooth: bool = False):
     """Seeded full-size oracle whose MLP masters are fp16-representable (see O.snap_mlp_weights_fp16): the fp32-FMA and
     the tensor-core kernels must both reproduce it, and tests/golden/ref_full_*.npz hold the unmodified reference's
     results for exactly these parameters."""
     from oracle import lidar4d_oracle as O
     orc = O.build_seeded(full_config(levels), seed, flow_last_std=0.02)
-    return O.snap_mlp_weights_fp16(orc)
+    O.snap_mlp_weights_fp16(orc)
+    return O.band_limit_tables(orc) if smooth else orc
 
 
-def grad_errors(a, b):
-    """(max|a-b| / max|b|,  ||a-b|| / ||b||,  worst element-wise excess over 1e-3*|b| + 1e-5*max|b|)."""
+def grad_errors(a, b, tol: float = 1e-4):
+    """(max|a-b| / max|b|,  ||a-b|| / ||b||,  fraction of entries with |a-b| > tol * max|b|)."""
     a = torch.as_tensor(a).detach().double().reshape(-1).cpu()
     b = torch.as_tensor(b).detach().double().reshape(-1).cpu()
     if a.numel() == 0:
         return 0.0, 0.0, 0.0
     d = (a - b).abs()
     bmax = float(b.abs().max()) + 1e-30
-    mixed = float((d - (1e-3 * b.abs() + 1e-5 * bmax)).max())
-    return float(d.max() / bmax), float(d.norm() / (b.norm() + 1e-30)), mixed
+    return float(d.max() / bmax), float(d.norm() / (b.norm() + 1e-30)), float((d > tol * bmax).double().mean())

@@ -18,12 +18,12 @@ def load(name):
     return np.load(os.path.join(GOLD, name + ".npz"))
 
 
-FULL_CASES = ["ref_full_L16_interior", "ref_full_L8_interior", "ref_full_L16_first", "ref_full_L8_last"]
+FULL_CASES = ["ref_full_L16_interior", "ref_full_L16_smooth", "ref_full_L8_smooth", "ref_full_L16_first", "ref_full_L8_last"]
 
 
 def oracle_case(fx):
     if "levels" in fx.files:
-        orc = full_oracle(int(fx["levels"]), int(fx["seed"]))
+        orc = full_oracle(int(fx["levels"]), int(fx["seed"]), bool(int(fx["smooth"])))
     else:
         orc = O.build_seeded(small_config(), int(fx["seed"]), flow_last_std=0.02)
     chk = sum(float(v.double().sum()) for v in orc.ref_state_dict().values())
@@ -113,3 +113,12 @@ def test_planes_restatement_matches_grid_sample_directly():
     expect = p01[:, iy, ix] * orc.p("planes_encoder.planes.0.1")[0][:, iz, ix] * orc.p("planes_encoder.planes.0.3")[0][:, iz, iy]
     assert torch.allclose(v, expect, rtol=1e-5, atol=1e-6)
     assert st.shape == (50, 32)
+
+
+def test_z_grid_restatement_matches_cuda_linspace_dump():
+    """tests/golden/cuda_linspace.npz = torch.linspace(0, 1, S, device="cuda") dumped on a B200 (scripts/diag_fullsize.py):
+    the oracle's (and, through tests/test_hostsim_parity.py, the kernels') z grid is bit-exact with the grid the reference
+    gets on its GPU path (renderer.py:77)."""
+    fx = load("cuda_linspace")
+    for S in fx.files:
+        assert np.array_equal(O.sample_lin(int(S)), fx[S]), S
