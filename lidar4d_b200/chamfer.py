@@ -32,6 +32,7 @@ class chamfer_3DFunction(Function):
         if xyz1.shape[0] != xyz2.shape[0]:
             raise ValueError("batch sizes differ")
         lib = _capi.load_library()
+        ctx.in_dtypes = (xyz1.dtype, xyz2.dtype)
         xyz1 = xyz1.contiguous().float()
         xyz2 = xyz2.contiguous().float()
         b, n, _ = xyz1.shape
@@ -68,7 +69,7 @@ class chamfer_3DFunction(Function):
                                           idx1.data_ptr(), idx2.data_ptr(), gx1.data_ptr(), gx2.data_ptr(),
                                           torch.cuda.current_stream(dev).cuda_stream)
         _capi.check(lib, rc, "l4d_chamfer_backward")
-        return gx1, gx2
+        return gx1.to(ctx.in_dtypes[0]), gx2.to(ctx.in_dtypes[1])      # gradients in the inputs' dtype (fp16 clouds under autocast)
 
 
 class chamfer_3DDist(nn.Module):

@@ -102,3 +102,52 @@ def test_chamfer_properties_full_size():
     (o1.sum() + o2.sum()).backward()
     tot = a2.grad.sum(1) + b2.grad.sum(1)
     assert float(tot.abs().max()) < 1e-2 * float(a2.grad.abs().sum())
+
+
+# ---- the reference's OWN kernel (utils/chamfer3D/chamfer3D.cu compiled in place for sm_100a by oracle/build_ref.py) -------
+def _ref_ext():
+    from oracle import build_ref
+    return build_ref.load()
+
+
+def test_reference_extension_was_built():
+    """oracle/_ref/chamfer_3D_ref.so is the reference's chamfer extension built by the committed recipe; it travels to
+    the GPU box with the snapshot (the GPU box has no /root/reference)."""
+    import os
+    from oracle import build_ref
+    build_ref.build()                    # no-op without /root/reference
+    assert os.path.exists(build_ref.so_path()), "run `python oracle/build_ref.py` in the build container"
+
+
+REF_CASES = CASES + [(1, 4096, 4096, 11, True), (1, 60000, 50000, 12, False), (2, 1, 1, 13, False)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,n,m,seed,dup", REF_CASES)
+def test_chamfer_bit_exact_against_reference_kernel(b, n, m, seed, dup):
+    """Distances AND indices of l4d_chamfer_forward equal NmDistanceKernel's (chamfer3D.cu:11-133) bit for bit - also on
+    exact duplicates (ties -> smallest index) - and the gradients equal NmDistanceGradKernel's (:154-174) to fp32
+    atomics re-ordering.  This pins oracle/chamfer_oracle.py's assumed fma contraction as well."""
+    from lidar4d_b200.chamfer import chamfer_3DDist
+    ext = _ref_ext()
+    dev = torch.device("cuda:0")
+    x1, x2 = _clouds(b, n, m, seed, dup)
+    t1 = torch.from_numpy(x1).to(dev).requires_grad_(True)
+    t2 = torch.from_numpy(x2).to(dev).requires_grad_(True)
+    d1, d2, i1, i2 = chamfer_3DDist()(t1, t2)
+    r1, r2 = torch.zeros(b, n, device=dev), torch.zeros(b, m, device=dev)
+    j1, j2 = torch.zeros(b, n, dtype=torch.int32, device=dev), torch.zeros(b, m, dtype=torch.int32, device=dev)
+    assert ext.forward(t1.detach(), t2.detach(), r1, r2, j1, j2) == 1        # dist_chamfer_3D.py:52
+    torch.cuda.synchronize()
+    assert torch.equal(d1.detach(), r1) and torch.equal(d2.detach(), r2)
+    assert torch.equal(i1, j1) and torch.equal(i2, j2)
+    o1, o2, oi1, oi2 = CO.chamfer_forward(x1, x2)                            # the numpy oracle agrees with the real kernel
+    assert np.array_equal(r1.cpu().numpy(), o1) and np.array_equal(j2.cpu().numpy(), oi2)
+    g = torch.Generator().manual_seed(seed)
+    g1, g2 = torch.randn(b, n, generator=g).to(dev), torch.randn(b, m, generator=g).to(dev)
+    ((d1 * g1).sum() + (d2 * g2).sum()).backward()
+    gx1, gx2 = torch.zeros_like(t1), torch.zeros_like(t2)
+    assert ext.backward(t1.detach(), t2.detach(), gx1, gx2, g1, g2, j1, j2) == 1   # dist_chamfer_3D.py:70-72
+    torch.cuda.synchronize()
+    for got, ref in ((t1.grad, gx1), (t2.grad, gx2)):
+        assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-12

@@ -171,6 +171,7 @@ def test_checkpoint_round_trip(dev):
                  near_lidar=c.near_lidar, far_lidar=c.far_lidar, hash_size_dynamic=c.hash_size_dynamic,
                  flow_base_resolution=c.flow_base_resolution, flow_max_resolution=c.flow_max_resolution,
                  flow_log2_hashmap_size=c.flow_log2_hashmap_size).to(dev)
+    m2.set_mlp_fp16(m._engine.mlp_fp16)
     with torch.no_grad():
         before = _render(m2, dev)["depth_lidar"].clone()
     res = m2.load_state_dict(torch.load(buf, weights_only=False)["model"], strict=False)
@@ -182,6 +183,7 @@ def test_checkpoint_round_trip(dev):
 
 def test_launch_counter_counts_kernels(dev):
     orc, m = _model()
+    m.set_mlp_fp16(True)
     n0 = m.gpu_launches
     with torch.no_grad():
         _render(m, dev)

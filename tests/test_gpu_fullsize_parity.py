@@ -126,12 +126,15 @@ def test_full_size_vs_reference_golden_and_oracle(dev, name, mode, pipeline):
         n_ref, n_got = float(g_ref.double().norm()), float(got[k].double().norm())
         ok = ok and abs(n_got - n_ref) <= norm_tol * n_ref + 1e-30
         if g_ref.numel() > 70000:          # the touched-entry set is index arithmetic: exact, whatever the values do
-            same = torch.equal(got[k].cpu().reshape(-1) != 0, g_ref.reshape(-1) != 0)
-            if not same:                   # entries whose oracle value is an exact 0 * x may legitimately differ in sign of zero only
-                diff = (got[k].cpu().reshape(-1) != 0) != (g_ref.reshape(-1) != 0)
-                same = float(got[k].cpu().reshape(-1)[diff].abs().max()) < 1e-12 * (float(g_ref.abs().max()) + 1e-30) and \
-                    float(g_ref.reshape(-1)[diff].abs().max()) < 1e-12 * (float(g_ref.abs().max()) + 1e-30)
-            ok = ok and same
+            a, b = got[k].cpu().reshape(-1), g_ref.reshape(-1)
+            diff = (a != 0) != (b != 0)
+            if bool(diff.any()):           # only entries whose value is a rounding-level cancellation may differ in being exactly 0
+                lim = 1e-6 * float(b.abs().max())
+                same = float(a[diff].abs().max()) <= lim and float(b[diff].abs().max()) <= lim and int(diff.sum()) <= 1e-4 * int((b != 0).sum()) + 2
+                if not same:
+                    report[k] += (f"support: {int(diff.sum())} entries differ, max |cuda| {float(a[diff].abs().max()):.2e} "
+                                  f"|oracle| {float(b[diff].abs().max()):.2e} of {float(b.abs().max()):.2e}",)
+                ok = ok and same
         if not ok:
             bad[k] = report[k]
     assert not bad, f"failing (max-rel, l2-rel, outlier fraction): {bad}"
