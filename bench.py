@@ -46,6 +46,13 @@ def parse():
     ap.add_argument("--rays", type=int, default=H_SWEEP * W_SWEEP, help="rays per step (sweep size)")
     ap.add_argument("--cpu-rays", type=int, default=64, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank renders --rays rays per step; strong: --rays is the GLOBAL batch, sharded over the ranks "
+                         "(BASELINE.json configs[2]: --scaling strong --rays 4096)")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="infer: BASELINE.json configs[3], forward-only render of one 64x2048 frame per step")
+    ap.add_argument("--eager-rays", type=int, default=1024,
+                    help="rays per step of the GPU-eager baseline leg (the reference's op graph in plain torch under fp16 autocast); 0 = skip")
     ap.add_argument("--pipeline", default="split", choices=["split", "fused"])
     ap.add_argument("--mlp", default="fp16", choices=["fp16", "fp32"],
                     help="fp16: MLP weights as fp16 working copies (as tiny-cuda-nn), tensor-core dense kernels; fp32: FMA")
@@ -265,11 +272,86 @@ def workload_config(args, note=None):
 # =============================================================================
 # GPU arm
 # =============================================================================
+def sector_counts(cfg):
+    """Algorithmic 32-byte sector requests per sample of the gather-type kernels (every divergent gather touches one
+    sector: 8 B static-hash corner, 16 B dynamic-hash slice pair / flow corner, 32 B plane texel) and vector reductions
+    (RED.E.ADD.F32x4 lane-ops) of the scatter-type kernels.  DESIGN.md 4.3."""
+    L = cfg.n_levels_hash
+    planes_s, planes_d = 4 * 3 * 4, 3 * (4 * 3 * 4)
+    return {
+        "k_fwd_gather": {"unit": "sectors", "per_sample": L * 8 + 3 * 3 * L * 4 + planes_s + planes_d},
+        "k_fwd_flow_tc": {"unit": "sectors", "per_sample": 8 * 8},
+        "k_bwd_scatter_static": {"unit": "red128", "per_sample": L * 8},
+        "k_bwd_flowgrid": {"unit": "red128", "per_sample": 8 * 8 * 0.5},
+    }
+
+
+def micro_peaks():
+    """Measured ceilings of the units that actually bind the kernels (profiles/r02_micro_peaks.json, from
+    scripts/micro/{gather,red}_bench.cu on a B200 of this pool): divergent L2-resident sector gathers, RED.128 lane-ops."""
+    p = os.path.join(ROOT, "profiles", "r02_micro_peaks.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return {}
+
+
+def ncu_binding():
+    p = os.path.join(ROOT, "profiles", "ncu_binding.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def gpu_eager_baseline(levels, n_rays, dev):
+    """SURVEY.md 8(d)(ii) / BASELINE.md 3 'B-gpu-eager': the reference's op graph (the oracle = its plain-torch restatement,
+    pinned to the reference modules to 1e-6; the modules themselves live in /root/reference, which does not exist on the GPU
+    box) executed eagerly on THIS GPU under fp16 autocast as runner.py:497 does, fwd + bwd + Adam, bounded sample.
+    A baseline leg like cpu_baseline: the only thing here that touches oracle/ on a GPU."""
+    from lidar4d_b200.rays import synthetic_sweep
+    try:
+        orc, _ = build_oracle(levels)
+        orc = orc.to(dev)
+        opt = torch.optim.Adam(orc.parameters(), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+        scaler = torch.amp.GradScaler("cuda")
+        ro, rd, t = synthetic_sweep(7, N_FRAMES, H_SWEEP, W_SWEEP)
+        sel = np.linspace(0, ro.shape[0] - 1, n_rays).astype(np.int64)
+        ro_t, rd_t = torch.from_numpy(ro[sel]).to(dev), torch.from_numpy(rd[sel]).to(dev)
+
+        def one(seed):
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = orc.render(ro_t, rd_t, float(t), num_steps=S_STEPS, perturb=True, seed=seed)
+                loss = (out["depth_lidar"] - 0.3).abs().mean() + ((out["image_lidar"] - 0.5) ** 2).mean()
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+        for i in range(2):
+            one(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        torch.cuda.reset_peak_memory_stats()
+        e0.record()
+        for i in range(reps):
+            one(10 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        res = {"value": n_rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "rays_per_step": n_rays,
+               "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9, "kind": "port",
+               "what": "oracle (plain-torch restatement of the reference op graph on the tcnn spec) in GPU eager mode, fp16 autocast + "
+                       "GradScaler, fwd+bwd+Adam; tiny-cuda-nn itself cannot be built here"}
+        del orc, opt
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:          # a baseline leg must never take the bench line down
+        return {"value": None, "unit": "rays/s", "error": repr(e)[:200]}
+
+
 def run_b200(args):
     import torch.distributed as dist
     from lidar4d_b200 import LiDAR4D
     from lidar4d_b200.rays import synthetic_sweep
-    from lidar4d_b200.parallel import RayShardedDP
+    from lidar4d_b200.parallel import RayShardedDP, shard_range
+    from lidar4d_b200.optim import Adam          # main_lidar4d.py:298-300 recipe, one launch fused with the fp16 table refresh
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -280,6 +362,10 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    infer = args.mode == "infer"
+    if infer and args.rays == H_SWEEP * W_SWEEP:
+        args.rays = 64 * 2048                        # BASELINE.json configs[3]
+    strong = args.scaling == "strong" and not infer
 
     torch.manual_seed(0)
     model = LiDAR4D(**model_kwargs(args.levels)).to(dev)
@@ -288,34 +374,41 @@ def run_b200(args):
     model.pipeline = args.pipeline
     model.set_mlp_fp16(args.mlp == "fp16")
     dp = RayShardedDP(model, world_size=world, rank=rank)
-    from lidar4d_b200.optim import Adam          # main_lidar4d.py:298-300 recipe, one launch fused with the fp16 table refresh
     opt = Adam(model, model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
-    n_rays, rb = args.rays, args.ray_batch
+    rb = args.ray_batch
+    # rays of this rank per step: weak = a whole sweep each, strong = a contiguous 1/R shard of the global batch
+    lo, hi = shard_range(args.rays, world, rank) if strong else (0, args.rays)
+    n_rays = hi - lo
+    global_rays = args.rays if strong else args.rays * world
+    W_frame = 2048 if infer else W_SWEEP
 
-    # host-side inputs in pinned memory (one sweep per frame), targets on the host as well
+    # host-side inputs in pinned memory (one sweep per frame)
     frames = []
     for k in range(min(N_FRAMES, args.warmup + args.steps + 1)):
-        ro, rd, t = synthetic_sweep((k * world + rank) % N_FRAMES, N_FRAMES, H_SWEEP, W_SWEEP)
-        ro, rd = ro[:n_rays], rd[:n_rays]
-        frames.append((torch.from_numpy(ro).pin_memory(), torch.from_numpy(rd).pin_memory(), float(t)))
+        fid = (k if strong else k * world + rank) % N_FRAMES
+        ro, rd, t = synthetic_sweep(fid, N_FRAMES, H_SWEEP, W_frame)
+        ro, rd = ro[lo:hi] if strong else ro[:n_rays], rd[lo:hi] if strong else rd[:n_rays]
+        frames.append((torch.from_numpy(np.ascontiguousarray(ro)).pin_memory(), torch.from_numpy(np.ascontiguousarray(rd)).pin_memory(), float(t)))
     host_out = torch.empty(n_rays, 3).pin_memory()
+    ray_off0 = lo if strong else rank * n_rays
 
-    def step(i, e2e):
+    def inputs(i, e2e):
         ro_h, rd_h, t = frames[i % len(frames)]
         if e2e:
-            ro_d, rd_d = ro_h.to(dev, non_blocking=True), rd_h.to(dev, non_blocking=True)
-            step.cache = (ro_d, rd_d)
-        else:
-            if getattr(step, "resident", None) is None or step.resident[0] != i % len(frames):
-                step.resident = (i % len(frames), ro_h.to(dev), rd_h.to(dev))
-            ro_d, rd_d = step.resident[1], step.resident[2]
+            return ro_h.to(dev, non_blocking=True), rd_h.to(dev, non_blocking=True), t
+        if getattr(inputs, "resident", None) is None or inputs.resident[0] != i % len(frames):
+            inputs.resident = (i % len(frames), ro_h.to(dev), rd_h.to(dev))
+        return inputs.resident[1], inputs.resident[2], t
+
+    def train_step(i, e2e):
+        ro_d, rd_d, t = inputs(i, e2e)
         opt.zero_grad(set_to_none=True)
         tot = torch.zeros((), device=dev)
         outs = []
         for h in range(0, n_rays, rb):
             out = model.render(ro_d[None, h:h + rb], rd_d[None, h:h + rb], t, staged=False, num_steps=S_STEPS,
-                               perturb=True, ray_offset=rank * n_rays + h)
-            loss = ((out["depth_lidar"] - 0.3).abs().sum() + ((out["image_lidar"] - 0.5) ** 2).sum()) / (n_rays * world)
+                               perturb=True, ray_offset=ray_off0 + h)
+            loss = ((out["depth_lidar"] - 0.3).abs().sum() + ((out["image_lidar"] - 0.5) ** 2).sum()) / global_rays
             loss.backward()
             tot += loss.detach()
             if e2e:
@@ -326,6 +419,21 @@ def run_b200(args):
             host_out.copy_(torch.cat(outs, 0), non_blocking=True)
             return float(tot)            # device->host read of the step's loss (sync)
         return tot
+
+    def infer_step(i, e2e):
+        ro_d, rd_d, t = inputs(i, e2e)
+        with torch.no_grad():
+            out = model.render(ro_d[None], rd_d[None], t, staged=False, num_steps=S_STEPS, perturb=False, ray_offset=ray_off0)
+        if e2e:
+            host_out[:, 0:1].copy_(out["depth_lidar"].view(-1, 1), non_blocking=True)
+            host_out[:, 1:3].copy_(out["image_lidar"].view(-1, 2), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out["depth_lidar"]
+
+    step = infer_step if infer else train_step
+    if infer:
+        model.eval()
+        model.static_params(True)
 
     def barrier():
         if world > 1:
@@ -348,7 +456,7 @@ def run_b200(args):
             ms = float(tm)
         return ms, model.gpu_launches - l0
 
-    log(f"model ready (L={args.levels}), {n_rays} rays/step in launches of {rb}")
+    log(f"model ready (L={args.levels}), mode {args.mode}, {args.scaling} scaling: {n_rays} rays/step on this rank in launches of {rb}")
     for i in range(args.warmup):
         tw = time.perf_counter()
         step(i, False)
@@ -359,9 +467,10 @@ def run_b200(args):
         sampler.start()
     ms, launches = timed(False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else {}
-    log(f"timed: {ms / args.steps:.1f} ms/step")
+    log(f"timed: {ms / args.steps:.2f} ms/step")
     step(0, True)                                  # warm the e2e path (pinned copies)
     ms_e2e, _ = timed(True, args.steps, args.warmup)
+    peak_mem = torch.cuda.max_memory_allocated() / 1e9
 
     # ---- per-kernel durations for the roofline: CUDA events recorded by the library on the launch stream ----
     from lidar4d_b200 import _capi
@@ -369,78 +478,110 @@ def run_b200(args):
     ktimes = _capi.profile_kernels(lambda: [step(args.warmup + i, False) for i in range(2)])
     torch.cuda.synchronize()
 
-    # ---- the two density regimes and their measured attribute-mask fraction M/P ----
-    def mask_fraction():
-        keep = model.materialize_weights
-        model.materialize_weights = True
-        with torch.no_grad():
-            ro_h, rd_h, t = frames[0]
-            sel = torch.linspace(0, n_rays - 1, min(1024, n_rays)).long()
-            out = model.render(ro_h[sel].to(dev)[None], rd_h[sel].to(dev)[None], t, staged=False, num_steps=S_STEPS, perturb=False)
-            mf = float((out["weights"] > 1e-4).float().mean())
-        model.materialize_weights = keep
-        return mf
+    regimes = None
+    if not infer:
+        # ---- the two density regimes and their measured attribute-mask fraction M/P ----
+        def mask_fraction():
+            keep = model.materialize_weights
+            model.materialize_weights = True
+            with torch.no_grad():
+                ro_h, rd_h, t = frames[0]
+                sel = torch.linspace(0, n_rays - 1, min(1024, n_rays)).long()
+                out = model.render(ro_h[sel].to(dev)[None], rd_h[sel].to(dev)[None], t, staged=False, num_steps=S_STEPS, perturb=False)
+                mf = float((out["weights"] > 1e-4).float().mean())
+            model.materialize_weights = keep
+            return mf
 
-    regimes = {"init-like": {"mask_fraction": mask_fraction(), "rays_per_s": n_rays * world * args.steps / (ms * 1e-3)}}
-    with torch.no_grad():           # surface-like: positive, scaled sigma row => the weight mass sits in a few samples per ray
-        pz = model.sigma_net.params
-        off = 64 * model.cfg.sigma_in_pad
-        pz[off:off + 64] = pz[off:off + 64].abs() * 4.0
-    model._engine.ensure_staged()
-    step(0, False)
-    ms_s, _ = timed(False, 2, 1)
-    regimes["surface-like"] = {"mask_fraction": mask_fraction(), "rays_per_s": n_rays * world * 2 / (ms_s * 1e-3)}
-    log(f"regimes: {regimes}")
+        regimes = {"init-like": {"mask_fraction": mask_fraction(), "rays_per_s": global_rays * args.steps / (ms * 1e-3)}}
+        with torch.no_grad():           # surface-like: positive, scaled sigma row => the weight mass sits in a few samples per ray
+            pz = model.sigma_net.params
+            off = 64 * model.cfg.sigma_in_pad
+            pz[off:off + 64] = pz[off:off + 64].abs() * 4.0
+        step(0, False)
+        ms_s, _ = timed(False, 2, 1)
+        regimes["surface-like"] = {"mask_fraction": mask_fraction(), "rays_per_s": global_rays * 2 / (ms_s * 1e-3)}
+        log(f"regimes: {regimes}")
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    samples_per_launch = min(rb, n_rays) * S_STEPS
+    samples_per_launch = min(rb, n_rays) * S_STEPS if not infer else min(model.infer_ray_chunk, n_rays) * S_STEPS
     kbytes = kernel_bytes(model.cfg)
+    secs = sector_counts(model.cfg)
+    mp = micro_peaks()
+    nb = ncu_binding().get("kernels", {})
     kern = {}
     for name, ts in ktimes.items():
         avg = float(np.mean(ts))
         b = kbytes.get(name.replace("_tc", ""), None)
-        kern[name] = {"avg_ms": avg, "launches_timed": len(ts), "alg_bytes_per_sample": b,
-                      "achieved_gbs": (b * samples_per_launch / (avg * 1e-3) / 1e9) if b else None}
+        k = {"avg_ms": avg, "launches_timed": len(ts), "alg_bytes_per_sample": b,
+             "alg_gbs_l2_resident_not_a_dram_bound": (b * samples_per_launch / (avg * 1e-3) / 1e9) if b else None}
+        if name in secs:
+            u = secs[name]
+            rate = u["per_sample"] * samples_per_launch / (avg * 1e-3) / 1e9
+            ceil = mp.get("gather_gsectors_s" if u["unit"] == "sectors" else "red128_glaneops_s")
+            k["binding"] = {"unit": "G 32B-sector gathers/s (L2-resident, divergent)" if u["unit"] == "sectors" else "G RED.128 lane-ops/s (L2-resident)",
+                            "per_sample": u["per_sample"], "achieved": rate, "peak": ceil, "frac": (rate / ceil) if ceil else None}
+        if name in nb:
+            k["ncu"] = nb[name]            # pipe utilisation of this kernel from the committed ncu capture (profiles/)
+        kern[name] = k
     dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
-    roofline = None
     traffic = None
     try:        # dram__bytes_read+write of the dominant kernel from the committed ncu capture (same launch shape only)
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         if args.levels == 16 and tj["dram_bytes_per_launch"].get(dom) is not None:
-            # captured at 8192 rays per launch; every byte of these kernels is per-sample traffic
-            traffic = tj["dram_bytes_per_launch"][dom] * (min(rb, n_rays) / 8192.0)
+            traffic = tj["dram_bytes_per_launch"][dom] * (samples_per_launch / (float(tj.get("rays_per_launch", 8192)) * S_STEPS))
     except Exception:
         traffic = None
+    roofline = None
     if dom:
-        ach = kern[dom]["achieved_gbs"]
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src, "kernels": kern,
-                    "whole_forward_gbs": kbytes["forward"] * samples_per_launch / (sum(kern[k]["avg_ms"] for k in kern if "fwd" in k) * 1e-3) / 1e9,
-                    "whole_backward_gbs": kbytes["backward"] * samples_per_launch / (sum(kern[k]["avg_ms"] for k in kern if "bwd" in k) * 1e-3) / 1e9,
-                    "note": "achieved = algorithmic bytes (SURVEY 8(d) / DESIGN.md 4.3: every gather and every read-modify-write counted once) / measured "
-                            "duration; the fp16 tables and the live gradient slabs are L2-resident and shared reductions are folded after "
-                            "the scatter, so achieved exceeds the DRAM roofline (frac > 1) and `traffic` (ncu dram bytes per launch) is far lower: "
-                            "the binding limits are the L1TEX/LSU data pipe and L2 atomic throughput (profiles/*_ncu_summary.md)"}
-    total_rays = n_rays * world * args.steps
+        kd = kern[dom]
+        bind = kd.get("binding")
+        alg = kd["alg_gbs_l2_resident_not_a_dram_bound"]
+        dram_gbs = (traffic / (kd["avg_ms"] * 1e-3) / 1e9) if traffic else None
+        if bind and bind["frac"] is not None:
+            # the unit that binds the dominant kernel, in GB/s of 32-byte sectors (gathers) or 16-byte vector reductions
+            w = 32.0 if "sector" in bind["unit"] else 16.0
+            roofline = {"bound": bind["unit"], "kernel": dom, "achieved": bind["achieved"] * w, "peak": bind["peak"] * w,
+                        "unit": "GB/s", "frac": bind["frac"], "traffic": traffic,
+                        "peak_source": "measured: scripts/micro/*_bench.cu on this pool's B200 (profiles/r02_micro_peaks.json)"}
+        else:
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": dram_gbs, "peak": peak, "unit": "GB/s",
+                        "frac": (dram_gbs / peak) if dram_gbs else None, "traffic": traffic, "peak_source": peak_src,
+                        "achieved_is": "MEASURED dram bytes (ncu) / live duration: this kernel is bound by " +
+                                       str((kd.get("ncu") or {}).get("limiter", "on-chip units (profiles/*_ncu_summary.md)"))}
+        roofline.update({
+            "hbm": {"measured_dram_gbs": dram_gbs, "peak": peak, "frac": (dram_gbs / peak) if dram_gbs else None, "peak_source": peak_src,
+                    "algorithmic_gbs": alg, "note": "algorithmic bytes (SURVEY 8(d)) / duration; the fp16 tables and live gradient slabs "
+                                                    "are L2-resident, so this is NOT a DRAM bound and may exceed the HBM peak"},
+            "kernels": kern})
+    total_rays = global_rays * args.steps
     value = total_rays / (ms * 1e-3)
+    metric = ("inference rays/sec at 64x2048 rays x 768 samples" if infer else "training rays/sec at 64x1024 rays x 768 samples")
+    cfgd = workload_config(args)
+    cfgd.update({"rays_per_step": global_rays, "rays_per_rank": n_rays, "mode": args.mode,
+                 "optimizer": "lidar4d_b200.optim.Adam (one launch, fused fp16 table refresh)" if not infer else None})
     line = {
-        "metric": "training rays/sec at 64x1024 rays x 768 samples", "value": value, "unit": "rays/s",
+        "metric": metric, "value": value, "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": ("fp16 tables + fp16 MLP weights (tcgen05, hi/lo fp16 activations, fp32 accumulate)" if args.mlp == "fp16"
                   else "fp16 tables, fp32 MLPs") + "; fp32 planes, compositing and gradients", "data": "synthetic",
-        "config": workload_config(args),
+        "config": cfgd,
         "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n_rays * 6 * 4,
-                "d2h_bytes_per_step": n_rays * 3 * 4 + 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "regimes": regimes,
+                "d2h_bytes_per_step": n_rays * 3 * 4 + (0 if infer else 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "regimes": regimes, "peak_mem_gb": peak_mem,
     }
-    log(f"e2e {ms_e2e / args.steps:.1f} ms/step; kernels " + ", ".join(f"{k} {v['avg_ms']:.2f} ms" for k, v in kern.items()))
-    if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_subprocess(args)
+    log(f"e2e {ms_e2e / args.steps:.2f} ms/step; kernels " + ", ".join(f"{k} {v['avg_ms']:.2f} ms" for k, v in kern.items()))
+    if world == 1 and not infer:
+        if args.eager_rays > 0:
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_baseline(args.levels, args.eager_rays, dev)
+            log(f"gpu_eager_baseline: {line['gpu_eager_baseline']}")
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_subprocess(args)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -266,6 +266,14 @@ class _Engine:
             self.grad_work = torch.zeros(n, dtype=torch.uint8, device=self.device())
         return self.grad_work
 
+    def infer_workspace(self, n_rays: int, S: int):
+        """Persistent exchange workspace of no-grad renders through the split pipeline (grown on demand)."""
+        n = self._lib().l4d_saved_bytes(C.byref(self.ccfg), n_rays, S)
+        ws = getattr(self, "_infer_ws", None)
+        if ws is None or ws.device != self.device() or ws.numel() < n:
+            self._infer_ws = ws = torch.empty(n, dtype=torch.uint8, device=self.device())
+        return ws, n
+
     def reset_work(self):
         """Call after an exception inside a backward left the work buffer half-consumed."""
         if self.grad_work is not None:
@@ -369,19 +377,29 @@ class _RenderFn(torch.autograd.Function):
         fused = eng.owner.pipeline == "fused"
         rays.reserved = 1 if fused else 0
         saved, nsaved = None, 0
-        if train or not fused:          # the split pipeline exchanges features through this workspace
+        chunk = N
+        if train:
             nsaved = lib.l4d_saved_bytes(C.byref(eng.ccfg), N, S)
             saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
+        elif not fused:
+            # inference through the split pipeline: the kernels exchange feature tiles through a workspace; walk the rays
+            # in chunks over ONE persistent workspace (config 4: 131,072 rays per frame would otherwise need 160 GB)
+            chunk = min(N, int(eng.owner.infer_ray_chunk))
+            saved, nsaved = eng.infer_workspace(chunk, S)
         ev = eng._events("fwd")
         with torch.cuda.device(dev):
             if ev: ev[0].record()
-            rc = lib.l4d_render_forward(
-                C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(frame), C.byref(rays),
-                depth.data_ptr(), image.data_ptr(), wsum.data_ptr(),
-                weights.data_ptr() if want_weights else None, zvals.data_ptr() if want_weights else None,
-                saved.data_ptr() if saved is not None else None, nsaved, eng.stream())
+            for h in range(0, N, chunk):
+                n = min(chunk, N - h)
+                rays.rays_o, rays.rays_d, rays.n_rays = rays_o.data_ptr() + 12 * h, rays_d.data_ptr() + 12 * h, n
+                rays.ray_offset = int(ray_offset) + h
+                rc = lib.l4d_render_forward(
+                    C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(frame), C.byref(rays),
+                    depth.data_ptr() + 4 * h, image.data_ptr() + 8 * h, wsum.data_ptr() + 4 * h,
+                    weights.data_ptr() + 4 * h * S if want_weights else None, zvals.data_ptr() + 4 * h * S if want_weights else None,
+                    saved.data_ptr() if saved is not None else None, nsaved, eng.stream())
+                _capi.check(lib, rc, "l4d_render_forward")
             if ev: ev[1].record()
-        _capi.check(lib, rc, "l4d_render_forward")
         ctx.eng, ctx.frame, ctx.rays_args = eng, frame, (N, S, int(bool(perturb)), int(seed), int(ray_offset))
         ctx.saved, ctx.nsaved = (saved, nsaved) if train else (None, 0)
         ctx.fused = fused
@@ -571,6 +589,7 @@ class LiDAR4D(LiDAR_Renderer):
         # "arena": the backward kernels accumulate into the flat gradient arena that every .grad views (default);
         # "autograd": gradients are returned to autograd as tensors (torch.autograd.grad, hooks), slower
         self.grad_mode = "arena"
+        self.infer_ray_chunk = 2048        # rays per launch of a no-grad render (bounds the exchange workspace: 2.5 GB at L=16)
         self.jitter_seed = 0
         self._jitter_calls = 0
         self._engine = _Engine(self)

@@ -56,8 +56,36 @@ if os.path.exists(rep):
             mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[idx[m]]]
             tot += float(r[idx[m]].replace(",", "")) * mult
         traffic.setdefault(name, tot)
-    json.dump({"source": f"{tag}_ncu_summary.md", "config": "L=16, 8192 rays x 768 samples per launch", "dram_bytes_per_launch": traffic},
+    rays_per_launch = int(os.environ.get("PROFILE_RAYS", "8192"))
+    json.dump({"source": f"{tag}_ncu_summary.md", "config": f"L=16, {rays_per_launch} rays x 768 samples per launch",
+               "rays_per_launch": rays_per_launch, "dram_bytes_per_launch": traffic},
               open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
+    # which unit binds each kernel (bench.py quotes these next to its live timings)
+    units_pct = {"l1tex_lsu_data_pipe_pct": "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+                 "l2_throughput_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+                 "dram_throughput_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                 "tensor_pipe_pct": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                 "fma_pipe_pct": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+                 "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                 "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active"}
+    binding = {}
+    for r in rows[2:]:
+        name = re.sub(r"[<(].*", "", r[kn]).replace("void ", "").strip()
+        if name in binding:
+            continue
+        d = {}
+        for k, m in units_pct.items():
+            if m in idx:
+                try:
+                    d[k] = float(r[idx[m]].replace(",", ""))
+                except ValueError:
+                    pass
+        pipes = {k: v for k, v in d.items() if k in ("l1tex_lsu_data_pipe_pct", "l2_throughput_pct", "dram_throughput_pct", "tensor_pipe_pct", "fma_pipe_pct")}
+        if pipes:
+            top = max(pipes, key=pipes.get)
+            d["limiter"] = f"{top} = {pipes[top]:.0f} % of peak (ncu --set full, {tag})"
+        binding[name] = d
+    json.dump({"source": f"{tag}_ncu_summary.md", "kernels": binding}, open(os.path.join(P, "ncu_binding.json"), "w"), indent=1)
     out.append("## `ncu --set full --clock-control none --import-source on` capture (per launch)\n")
     out.append("| metric | " + " | ".join(re.sub(r"\(.*", "", r[kn]) for r in rows[2:]) + " | unit |")
     out.append("|---|" + "---|" * (len(rows) - 1))

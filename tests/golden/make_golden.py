@@ -270,9 +270,52 @@ def hash_index_vectors():
     print(f"wrote {out_path} ({os.path.getsize(out_path)/1024:.1f} KiB)")
 
 
+def trainer_case(seed=31):
+    """tests/golden/trainer_step.npz: loss / predictions of the UNMODIFIED Trainer.train_step and eval_step
+    (model/runner.py:166-434, flow loss on) on the reference model-on-shim, for tests/test_trainer_dropin.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_stubs
+    from trainer_mirror import default_opt, default_criterion, synthetic_batch
+    runner = ref_stubs.import_reference_runner()
+    orc = oracle_for(SMALL, seed)
+    ref = build_reference(SMALL)
+    ref.load_state_dict(orc.ref_state_dict(), strict=False)
+    S = 48
+    opt = default_opt(num_frames=6, num_steps=S, near_lidar=0.0105, far_lidar=0.851, fp16=False)
+    train, ev, pcs, ground = synthetic_batch(64, frame=2, num_frames=6, seed=1)
+    tr = runner.Trainer("t", opt, ref, criterion=default_criterion(), device=torch.device("cpu"), workspace=None,
+                        mute=True, fp16=False, use_checkpoint="scratch")
+    tr.pc_list, tr.pc_ground_list = pcs, ground
+    N = train["rays_o_lidar"].shape[1]
+    u = torch.from_numpy(O.jitter_uniform(seed, np.arange(N), S))
+    orig_rand, orig_cuda = torch.rand, torch.Tensor.cuda
+    # jitter (renderer.py:84) from the repo's counter-based stream; every other torch.rand call is the real one
+    def rand(*a, **k):
+        shape = tuple(a[0]) if (len(a) == 1 and not isinstance(a[0], int)) else tuple(a)
+        return u.clone() if shape == (N, S) else orig_rand(*a, **k)
+    torch.rand = rand
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        torch.manual_seed(3)
+        out = tr.train_step(train)
+        tr.use_refine = False
+        with torch.no_grad():
+            e = tr.eval_step(ev)
+    finally:
+        torch.rand, torch.Tensor.cuda = orig_rand, orig_cuda
+    p = os.path.join(ROOT, "tests", "golden", "trainer_step.npz")
+    np.savez_compressed(p, seed=seed, train_loss=np.float64(out[4].item()), pred_depth=out[2].detach().numpy(),
+                        eval_loss=np.float64(e[6].item()), eval_depth=e[1].numpy())
+    print(f"wrote {p}: train loss {float(out[4]):.6f}, eval loss {float(e[6]):.6f}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--trainer-only" in sys.argv:
+        trainer_case()
+        sys.exit(0)
     hash_index_vectors()
+    trainer_case()
     # interior frame (both neighbours), perturb off
     run_case("ref_small_interior", time=0.4, n_rays_hw=(4, 12), num_steps=48, perturb=False, seed=3)
     # first frame (no backward neighbour), slice index integral (t*7 == 0)
