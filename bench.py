@@ -53,6 +53,9 @@ def parse():
                     help="infer: BASELINE.json configs[3], forward-only render of one 64x2048 frame per step")
     ap.add_argument("--eager-rays", type=int, default=1024,
                     help="rays per step of the GPU-eager baseline leg (the reference's op graph in plain torch under fp16 autocast); 0 = skip")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="CUDA streams the ray chunks of a step alternate over: the latency-bound tensor-core kernels of one chunk "
+                         "overlap the L1TEX/LSU-bound gather / scatter kernels of the next (1 = serial)")
     ap.add_argument("--pipeline", default="split", choices=["split", "fused"])
     ap.add_argument("--mlp", default="fp16", choices=["fp16", "fp32"],
                     help="fp16: MLP weights as fp16 working copies (as tiny-cuda-nn), tensor-core dense kernels; fp32: FMA")
@@ -262,7 +265,7 @@ def workload_config(args, note=None):
                      f"L={args.levels} 4D hash (2^19 static, 2^15/2^13/2^13 x8 time slices) + 6 hex-planes x4 scales + flow field, "
                      f"{N_FRAMES} frames",
          "rays_per_step": args.rays, "ray_batch": args.ray_batch, "n_levels_hash": args.levels,
-         "parallelism": f"ray-sharded dp{args.gpus}", "pipeline": getattr(args, "pipeline", None), "mlp": getattr(args, "mlp", None),
+         "parallelism": f"ray-sharded dp{args.gpus}", "streams": getattr(args, "streams", 1), "pipeline": getattr(args, "pipeline", None), "mlp": getattr(args, "mlp", None),
          "l2": "inputs larger than L2: fp16/fp32 working set > 126 MB plus > 1 GB of saved activations streamed per step"}
     if note:
         c["note"] = note
@@ -400,19 +403,47 @@ def run_b200(args):
             inputs.resident = (i % len(frames), ro_h.to(dev), rd_h.to(dev))
         return inputs.resident[1], inputs.resident[2], t
 
-    def train_step(i, e2e):
+    n_chunks = (n_rays + rb - 1) // rb
+    n_streams = max(1, min(args.streams, n_chunks))
+    side = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else []
+
+    def chunk(h, ro_d, rd_d, t, e2e, last):
+        out = model.render(ro_d[None, h:h + rb], rd_d[None, h:h + rb], t, staged=False, num_steps=S_STEPS,
+                           perturb=True, ray_offset=ray_off0 + h)
+        loss = ((out["depth_lidar"] - 0.3).abs().sum() + ((out["image_lidar"] - 0.5) ** 2).sum()) / global_rays
+        if last:
+            dp.final_backward(loss)          # the hash-table bucket starts reducing while the flow backward still runs
+        else:
+            loss.backward()
+        res = None
+        if e2e:
+            res = torch.cat([out["depth_lidar"].detach().view(-1, 1), out["image_lidar"].detach().view(-1, 2)], 1)
+        return loss.detach(), res
+
+    def train_step(i, e2e, streams=True):
         ro_d, rd_d, t = inputs(i, e2e)
         opt.zero_grad(set_to_none=True)
-        tot = torch.zeros((), device=dev)
-        outs = []
-        for h in range(0, n_rays, rb):
-            out = model.render(ro_d[None, h:h + rb], rd_d[None, h:h + rb], t, staged=False, num_steps=S_STEPS,
-                               perturb=True, ray_offset=ray_off0 + h)
-            loss = ((out["depth_lidar"] - 0.3).abs().sum() + ((out["image_lidar"] - 0.5) ** 2).sum()) / global_rays
-            loss.backward()
-            tot += loss.detach()
-            if e2e:
-                outs.append(torch.cat([out["depth_lidar"].detach().view(-1, 1), out["image_lidar"].detach().view(-1, 2)], 1))
+        main = torch.cuda.current_stream()
+        parts, outs = [], []
+        if side and streams:
+            model.prepare_grads()             # attach + clear the gradient arena once, before the streams fork
+            for st in side:
+                st.wait_stream(main)
+            for c, h in enumerate(range(0, n_rays, rb)):
+                with torch.cuda.stream(side[c % n_streams]):
+                    l, r = chunk(h, ro_d, rd_d, t, e2e, False)
+                    parts.append(l)
+                    outs.append(r)
+            for st in side:
+                main.wait_stream(st)
+            for x in parts + [r for r in outs if r is not None]:
+                x.record_stream(main)
+        else:
+            for h in range(0, n_rays, rb):
+                l, r = chunk(h, ro_d, rd_d, t, e2e, h + rb >= n_rays)
+                parts.append(l)
+                outs.append(r)
+        tot = torch.stack(parts).sum()
         dp.allreduce_grads()
         opt.step()
         if e2e:
@@ -475,7 +506,8 @@ def run_b200(args):
     # ---- per-kernel durations for the roofline: CUDA events recorded by the library on the launch stream ----
     from lidar4d_b200 import _capi
     torch.cuda.synchronize()
-    ktimes = _capi.profile_kernels(lambda: [step(args.warmup + i, False) for i in range(2)])
+    # (serial: the library's event marks time one stream)
+    ktimes = _capi.profile_kernels(lambda: [(train_step(args.warmup + i, False, streams=False) if not infer else step(args.warmup + i, False)) for i in range(2)])
     torch.cuda.synchronize()
 
     regimes = None

@@ -201,6 +201,16 @@ int    l4d_render_backward(const L4DConfig* cfg, const void* staged, const L4DFr
                            const float* g_wsum_or_null, const float* g_weights_or_null,
                            const L4DMasterGrads* grads, void* grad_work, size_t grad_work_bytes,
                            void* stream);
+/* Same; additionally records the CUDA event `ev_hash_done_or_null` (a cudaEvent_t) on `stream` at the point from which the
+ * hash_static / hash_dynamic gradient buffers are final (after the static scatter and the dynamic fold, before the flow
+ * backward): a data-parallel caller starts all-reducing that bucket - 60 % of the gradient bytes - on a side stream while the
+ * rest of the backward still runs (lidar4d_b200/parallel.py). */
+int    l4d_render_backward_ex(const L4DConfig* cfg, const void* staged, const L4DFrame* frame,
+                              const L4DRays* rays, const void* saved, size_t saved_bytes,
+                              const float* g_depth, const float* g_image,
+                              const float* g_wsum_or_null, const float* g_weights_or_null,
+                              const L4DMasterGrads* grads, void* grad_work, size_t grad_work_bytes,
+                              void* ev_hash_done_or_null, void* stream);
 int    l4d_unstage_grads(const L4DConfig* cfg, const void* grad_work, size_t grad_work_bytes,
                          const L4DMasterGrads* grads, void* stream);
 
@@ -243,6 +253,18 @@ int    l4d_chamfer_forward(const float* xyz1, const float* xyz2, uint32_t b, uin
 int    l4d_chamfer_backward(const float* xyz1, const float* xyz2, uint32_t b, uint32_t n, uint32_t m,
                             const float* g_dist1, const float* g_dist2, const int32_t* idx1, const int32_t* idx2,
                             float* g_xyz1, float* g_xyz2, void* stream);
+
+/* --- SURVEY 8(f) "next" row 2: the thin layers either side of the render kernels, one launch each ------------------------
+ * l4d_lidar_rays replaces data/base_dataset.py:15-102 `get_lidar_rays` (+ the GT gather of kitti360_dataset.py:170-178):
+ * pose = DEVICE [4][4] row-major cam2world; inds = n flat pixel ids row*W+col (NULL = all H*W pixels in order, n = H*W);
+ * writes rays_o[n,3], rays_d[n,3] and, if gt != NULL, gt[n,C] = image[inds,C] (image = DEVICE [H*W,C]).
+ * l4d_lidar_loss replaces model/runner.py:179-213 (default criteria: L1 depth, MSE intensity / raydrop, label smoothing):
+ * ACCUMULATES the summed loss into *loss (zero it first) and writes d loss / d depth [n] and d loss / d image [n,2]. */
+int    l4d_lidar_rays(const float* pose, float fov_up, float fov, uint32_t H, uint32_t W, const long long* inds_or_null,
+                      uint32_t n, const float* image_or_null, uint32_t C, float* rays_o, float* rays_d, float* gt_or_null,
+                      void* stream);
+int    l4d_lidar_loss(const float* depth, const float* image2, const float* gt3, uint32_t n, float alpha_d, float alpha_r,
+                      float alpha_i, float smooth, float* loss, float* g_depth, float* g_image2, void* stream);
 
 /* --- profiling aid: while started, CUDA events are recorded on the launch stream around every kernel of
  *     l4d_render_forward / l4d_render_backward.  l4d_profile_stop returns the number of (kernel name, ms)

@@ -145,7 +145,7 @@ EXPORTS = [
     "l4d_abi_version", "l4d_last_error", "l4d_staged_bytes", "l4d_stage_params", "l4d_saved_bytes",
     "l4d_render_forward", "l4d_grad_work_bytes", "l4d_render_backward", "l4d_unstage_grads",
     "l4d_flow_forward", "l4d_flow_backward", "l4d_hash_indices", "l4d_density_forward", "l4d_attribute_forward", "l4d_chamfer_work_bytes", "l4d_chamfer_forward", "l4d_chamfer_backward", "l4d_tc_selftest", "l4d_tc_selftest2", "l4d_profile_start", "l4d_profile_stop",
-    "l4d_stage_params_ex", "l4d_adam_step", "l4d_launch_count",
+    "l4d_stage_params_ex", "l4d_adam_step", "l4d_launch_count", "l4d_render_backward_ex", "l4d_lidar_rays", "l4d_lidar_loss",
 ]
 
 
@@ -174,6 +174,9 @@ def declare(lib, prefix: str = "l4d_", host_sim: bool = False):
         f("render_forward").argtypes = [P(L4DConfig), V, P(L4DFrame), P(L4DRays), V, V, V, V, V, V, SZ, V]
         f("render_backward").argtypes = [P(L4DConfig), V, P(L4DFrame), P(L4DRays), V, SZ, V, V, V, V,
                                          P(L4DMasterGrads), V, SZ, V]
+        lib.l4d_render_backward_ex.argtypes = [P(L4DConfig), V, P(L4DFrame), P(L4DRays), V, SZ, V, V, V, V,
+                                               P(L4DMasterGrads), V, SZ, V, V]
+        lib.l4d_render_backward_ex.restype = C.c_int
         f("unstage_grads").argtypes = [P(L4DConfig), V, SZ, P(L4DMasterGrads), V]
         f("flow_forward").argtypes = [P(L4DConfig), V, P(L4DFrame), V, U32, V, V, V]
         f("flow_backward").argtypes = [P(L4DConfig), V, P(L4DFrame), V, U32, V, V, P(L4DMasterGrads), V, SZ, V]
@@ -196,6 +199,10 @@ def declare(lib, prefix: str = "l4d_", host_sim: bool = False):
         lib.l4d_adam_step.argtypes = [P(L4DConfig), V, V, V, V, C.c_uint64, P(L4DAdamGroup), U32, C.c_float, C.c_float,
                                       C.c_float, U32, C.c_float, U32, P(L4DMasterParams), V, SZ, V]
         lib.l4d_adam_step.restype = C.c_int
+        lib.l4d_lidar_rays.argtypes = [V, C.c_float, C.c_float, U32, U32, V, U32, V, U32, V, V, V, V]
+        lib.l4d_lidar_rays.restype = C.c_int
+        lib.l4d_lidar_loss.argtypes = [V, V, V, U32, C.c_float, C.c_float, C.c_float, C.c_float, V, V, V, V]
+        lib.l4d_lidar_loss.restype = C.c_int
         lib.l4d_launch_count.argtypes = []
         lib.l4d_launch_count.restype = C.c_uint64
         lib.l4d_profile_start.argtypes = []

@@ -1123,10 +1123,21 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
   return L4D_OK;
 }
 
+extern "C" int l4d_render_backward_ex(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
+                                      const void* saved, size_t saved_bytes, const float* g_depth, const float* g_image,
+                                      const float* g_wsum, const float* g_weights, const L4DMasterGrads* grads,
+                                      void* grad_work, size_t grad_work_bytes, void* ev_hash_done, void* stream);
 extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
                                    const void* saved, size_t saved_bytes, const float* g_depth, const float* g_image,
                                    const float* g_wsum, const float* g_weights, const L4DMasterGrads* grads,
                                    void* grad_work, size_t grad_work_bytes, void* stream) {
+  return l4d_render_backward_ex(cfg, staged, frame, rays, saved, saved_bytes, g_depth, g_image, g_wsum, g_weights, grads, grad_work,
+                                grad_work_bytes, nullptr, stream);
+}
+extern "C" int l4d_render_backward_ex(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
+                                      const void* saved, size_t saved_bytes, const float* g_depth, const float* g_image,
+                                      const float* g_wsum, const float* g_weights, const L4DMasterGrads* grads,
+                                      void* grad_work, size_t grad_work_bytes, void* ev_hash_done, void* stream) {
   int rc = check_config(cfg);
   if (rc != L4D_OK) return rc;
   rc = check_rays(rays);
@@ -1184,6 +1195,8 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
                                                single ? 1.0f : frame->cur.w_lo, frame->cur.w_hi);
       }
       prof_mark(st, "k_fold_dynamic");
+      // hash_static and hash_dynamic gradients are final from here on (the flow backward below only touches the flow net)
+      if (ev_hash_done) L4D_CUDA(cudaEventRecord((cudaEvent_t)ev_hash_done, st));
     }
     if (frame->has_fwd || frame->has_bwd) {     // with no neighbour frame nothing reaches the flow field
       if (cfg->mlp_fp16) {
@@ -1229,6 +1242,7 @@ extern "C" int l4d_render_backward(const L4DConfig* cfg, const void* staged, con
   if (grid > L4D_BWD_SCRATCH_CTAS) grid = L4D_BWD_SCRATCH_CTAS;
   ++g_launches; k_render_bwd<L4D_NT><<<grid, L4D_NT, smem, st>>>(A);
   prof_mark(st, "k_render_bwd");
+  if (ev_hash_done) L4D_CUDA(cudaEventRecord((cudaEvent_t)ev_hash_done, st));
   L4D_CUDA(cudaGetLastError());
   return L4D_OK;
 }
@@ -1361,6 +1375,7 @@ extern "C" int l4d_tc_selftest2(const void* A, const void* B, float* Cout, uint3
 }
 
 #include "l4d_chamfer.cuh"
+#include "l4d_rays.cuh"
 
 #ifdef L4D_PHASE_CLOCKS
 // debug build only: per-phase clock sums of k_bwd_dense_tc (thread 0 of every CTA), cleared on read
@@ -1372,3 +1387,28 @@ extern "C" int l4d_debug_phase_clocks(unsigned long long* out32) {
   return 0;
 }
 #endif
+
+
+// =============================================================================
+// ray generation + ground-truth gather, and the main-loss epilogue (l4d_rays.cuh)
+// =============================================================================
+extern "C" int l4d_lidar_rays(const float* pose, float fov_up, float fov, uint32_t H, uint32_t W, const long long* inds, uint32_t n,
+                              const float* image, uint32_t C, float* rays_o, float* rays_d, float* gt, void* stream) {
+  if (!pose || !rays_o || !rays_d || H == 0 || W == 0) return l4d_fail(L4D_EINVAL, "l4d_lidar_rays: null pointer or empty image");
+  if (gt && (!image || C == 0 || C > 8)) return l4d_fail(L4D_EINVAL, "l4d_lidar_rays: gt gather needs image and 1 <= C <= 8");
+  if (n == 0) return L4D_OK;
+  ++g_launches; k_lidar_rays<<<nblk(n), 256, 0, (cudaStream_t)stream>>>(pose, fov_up, fov, H, W, inds, n, image, C, rays_o, rays_d, gt);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}
+
+extern "C" int l4d_lidar_loss(const float* depth, const float* image, const float* gt, uint32_t n, float alpha_d, float alpha_r,
+                              float alpha_i, float smooth, float* loss, float* g_depth, float* g_image, void* stream) {
+  if (!depth || !image || !gt || !loss || !g_depth || !g_image) return l4d_fail(L4D_EINVAL, "l4d_lidar_loss: null pointer");
+  if (n == 0) return L4D_OK;
+  int grid = nblk(n);
+  if (grid > 4 * sm_count()) grid = 4 * sm_count();
+  ++g_launches; k_lidar_loss<<<grid, 256, 0, (cudaStream_t)stream>>>(depth, image, gt, n, alpha_d, alpha_r, alpha_i, smooth, loss, g_depth, g_image);
+  L4D_CUDA(cudaGetLastError());
+  return L4D_OK;
+}

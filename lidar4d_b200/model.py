@@ -140,11 +140,11 @@ class _Engine:
         self.static_params = False # True: skip the content check of no-grad calls (tight inference loops)
         self.flat_p = None
         self.flat_g = None
-        self.grad_work = None
+        self._works = {}
         self.offsets = None        # name -> (offset, numel) in floats
         self.total = 0
         self._gtab = None
-        self._launch_base = 0
+        self.hash_grads_hook = None  # (torch.cuda.Event, callable): see parallel.RayShardedDP.final_backward
         self.timing = None         # {'fwd': [(ev0, ev1)], 'bwd': [...]}: CUDA events around the fused kernels
 
     def set_mlp_fp16(self, on: bool):
@@ -260,11 +260,20 @@ class _Engine:
 
     def work(self):
         """Persistent zero-initialised gradient work buffer (plane / MLP grads in working layout, slice-independent
-        hash accumulators).  Every kernel that consumes a region clears it again."""
-        if self.grad_work is None or self.grad_work.device != self.device():
+        hash accumulators) of the CURRENT stream: every kernel that consumes a region clears it again, so launches
+        that overlap on different streams need their own (a fold kernel of one must not clear what the scatter of the
+        other is still adding)."""
+        key = (self.device(), self.stream())
+        w = self._works.get(key)
+        if w is None:
             n = self._lib().l4d_grad_work_bytes(C.byref(self.ccfg))
-            self.grad_work = torch.zeros(n, dtype=torch.uint8, device=self.device())
-        return self.grad_work
+            w = self._works[key] = torch.zeros(n, dtype=torch.uint8, device=self.device())
+        return w
+
+    def reset_work(self):
+        """Call after an exception inside a backward left a work buffer half-consumed."""
+        for w in self._works.values():
+            w.zero_()
 
     def infer_workspace(self, n_rays: int, S: int):
         """Persistent exchange workspace of no-grad renders through the split pipeline (grown on demand)."""
@@ -273,11 +282,6 @@ class _Engine:
         if ws is None or ws.device != self.device() or ws.numel() < n:
             self._infer_ws = ws = torch.empty(n, dtype=torch.uint8, device=self.device())
         return ws, n
-
-    def reset_work(self):
-        """Call after an exception inside a backward left the work buffer half-consumed."""
-        if self.grad_work is not None:
-            self.grad_work.zero_()
 
     # ---- staging ----------------------------------------------------------------
     def invalidate_staged(self):
@@ -435,14 +439,18 @@ class _RenderFn(torch.autograd.Function):
         ev = eng._events("bwd")
         with torch.cuda.device(dev):
             if ev: ev[0].record()
-            rc = lib.l4d_render_backward(
+            hook = eng.hash_grads_hook if arena else None      # (event, callback) armed by RayShardedDP for the step's last backward
+            rc = lib.l4d_render_backward_ex(
                 C.byref(eng.ccfg), eng.staged.data_ptr(), C.byref(ctx.frame), C.byref(rays),
                 ctx.saved.data_ptr(), ctx.nsaved, g_depth.data_ptr(), g_image.data_ptr(),
                 g_wsum.data_ptr() if g_wsum is not None else None,
                 g_weights.data_ptr() if g_weights is not None else None,
-                C.byref(tab), work.data_ptr(), work.numel(), eng.stream())
+                C.byref(tab), work.data_ptr(), work.numel(), hook[0].cuda_event if hook else None, eng.stream())
             if ev: ev[1].record()
             _capi.check(lib, rc, "l4d_render_backward")
+            if hook:
+                eng.hash_grads_hook = None
+                hook[1]()
             rc = lib.l4d_unstage_grads(C.byref(eng.ccfg), work.data_ptr(), work.numel(), C.byref(tab), eng.stream())
             _capi.check(lib, rc, "l4d_unstage_grads")
         ctx.saved = None
@@ -609,6 +617,15 @@ class LiDAR4D(LiDAR_Renderer):
         ``load_state_dict`` and anything done before a ``torch.no_grad()`` render (torch_ema ``copy_to``/``restore``
         around evaluation, runner.py:565-567,680) are detected automatically."""
         self._engine.invalidate_staged()
+        return self
+
+    def prepare_grads(self):
+        """Attach every parameter's .grad to the flat gradient arena (clearing it if the grads were None) on the current
+        stream.  Call once after ``zero_grad`` when the backward passes of one optimiser step are spread over several
+        CUDA streams, before those streams fork: otherwise the first backward to run would clear the arena on ITS stream."""
+        self._engine._require_cuda()
+        self._engine.ensure_staged()          # a pending re-staging must not happen on one of the forked streams either
+        self._engine.attach_grads()
         return self
 
     def static_params(self, on: bool = True):

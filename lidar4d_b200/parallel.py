@@ -27,7 +27,7 @@ def shard_range(n_rays: int, world_size: int, rank: int) -> Tuple[int, int]:
 def flat_grads(params: List[torch.Tensor]):
     """Return (flat, needs_copy_back).  When every .grad is a view into ONE
     storage (the flat arena the backward kernel accumulated into, see
-    model._Engine.new_grad_arena) that storage is reduced in place - a single
+    model._Engine.attach_grads) that storage is reduced in place - a single
     collective with no packing copies; otherwise the gradients are packed."""
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
@@ -48,6 +48,7 @@ class RayShardedDP:
         self.model = model
         self.world_size = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.rank = rank if rank is not None else (dist.get_rank() if dist.is_initialized() else 0)
+        self._comm, self._event, self._early = None, None, None
 
     def params(self) -> List[torch.Tensor]:
         return [p for p in self.model.parameters() if p.requires_grad and p.numel() > 0]
@@ -65,11 +66,47 @@ class RayShardedDP:
         ro, rd, off = self.shard(rays_o, rays_d)
         return self.model.render(ro, rd, time, ray_offset=off, **kw)
 
+    # ---- overlapped reduction -----------------------------------------------------------------------------------
+    def final_backward(self, loss: torch.Tensor) -> None:
+        """`loss.backward()` for the LAST backward of an optimiser step.  The backward kernels record an event once the
+        hash_static / hash_dynamic gradients are final (60 % of the gradient bytes; the flow-net backward still has to
+        run); that bucket's all-reduce starts behind the event on a side stream and overlaps the rest of the backward.
+        `allreduce_grads()` afterwards reduces the remaining buckets and joins the side stream."""
+        eng = getattr(self.model, "_engine", None)
+        if self.world_size == 1 or eng is None or not loss.is_cuda or getattr(self.model, "grad_mode", "") != "arena":
+            loss.backward()
+            return
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=loss.device)
+            self._event = torch.cuda.Event()
+            self._event.record()                      # materialise the cudaEvent_t handle
+        self._early = None
+
+        def start_bucket():
+            lo = eng.offsets["hash_encoder.hash_static.params"][0]
+            hi = eng.offsets["flow_net.grid_enc.params"][0]
+            self._comm.wait_event(self._event)
+            with torch.cuda.stream(self._comm):
+                dist.all_reduce(eng.flat_g[lo:hi], op=dist.ReduceOp.SUM)
+            self._early = (lo, hi)
+
+        eng.hash_grads_hook = (self._event, start_bucket)
+        loss.backward()
+        eng.hash_grads_hook = None                    # not consumed (e.g. the loss did not reach the renderer)
+
     @torch.no_grad()
     def allreduce_grads(self) -> None:
         if self.world_size == 1:
             return
         params = self.params()
+        eng = getattr(self.model, "_engine", None)
+        early, self._early = getattr(self, "_early", None), None
+        if early is not None and eng is not None and eng.flat_g is not None:
+            lo, hi = early
+            dist.all_reduce(eng.flat_g[:lo], op=dist.ReduceOp.SUM)          # planes
+            dist.all_reduce(eng.flat_g[hi:], op=dist.ReduceOp.SUM)          # flow grid + MLPs
+            torch.cuda.current_stream().wait_stream(self._comm)
+            return
         # a parameter that got no gradient on this rank still takes part in the reduction
         for p in params:
             if p.grad is None:
@@ -82,4 +119,3 @@ class RayShardedDP:
                 n = p.grad.numel()
                 p.grad.copy_(flat[o:o + n].view_as(p.grad))
                 o += n
-

@@ -270,6 +270,24 @@ def hash_index_vectors():
     print(f"wrote {out_path} ({os.path.getsize(out_path)/1024:.1f} KiB)")
 
 
+def rays_case():
+    """tests/golden/lidar_rays.npz: the reference's own get_lidar_rays (data/base_dataset.py:15-102, imported unchanged)
+    for a rotated / translated pose, all pixels of an 8 x 32 sweep."""
+    sys.path.insert(0, REF)
+    from data.base_dataset import get_lidar_rays
+    g = np.random.default_rng(5)
+    q, _ = np.linalg.qr(g.normal(size=(3, 3)))
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, :3] = (q * np.sign(np.linalg.det(q))).astype(np.float32)
+    pose[:3, 3] = [0.12, -0.3, 0.05]
+    H, W = 8, 32
+    r = get_lidar_rays(torch.from_numpy(pose)[None], [2.0, 26.9], H, W, -1)
+    p = os.path.join(ROOT, "tests", "golden", "lidar_rays.npz")
+    np.savez_compressed(p, pose=pose, H=H, W=W, fov_up=2.0, fov=26.9, rays_o=r["rays_o"][0].numpy(), rays_d=r["rays_d"][0].numpy(),
+                        inds=r["inds"][0].numpy())
+    print(f"wrote {p}")
+
+
 def trainer_case(seed=31):
     """tests/golden/trainer_step.npz: loss / predictions of the UNMODIFIED Trainer.train_step and eval_step
     (model/runner.py:166-434, flow loss on) on the reference model-on-shim, for tests/test_trainer_dropin.py."""
@@ -313,9 +331,11 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     if "--trainer-only" in sys.argv:
         trainer_case()
+        rays_case()
         sys.exit(0)
     hash_index_vectors()
     trainer_case()
+    rays_case()
     # interior frame (both neighbours), perturb off
     run_case("ref_small_interior", time=0.4, n_rays_hw=(4, 12), num_steps=48, perturb=False, seed=3)
     # first frame (no backward neighbour), slice index integral (t*7 == 0)

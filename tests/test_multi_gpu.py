@@ -25,13 +25,14 @@ orc = O.build_seeded(small_config(), 21, flow_last_std=0.02)
 ro, rd = test_rays(4, 9)
 N, S, t = ro.shape[0], 200, 0.4
 ro_t, rd_t = torch.from_numpy(ro)[None].cuda(), torch.from_numpy(rd)[None].cuda()
-def grads(model, dp):
+def grads(model, dp, overlapped=False):
     model.zero_grad(set_to_none=True)
     model._jitter_calls = 0
     out = dp.render(ro_t, rd_t, torch.tensor([[t]]), num_steps=S, perturb=True) if dp else \
           model.render(ro_t, rd_t, torch.tensor([[t]]), num_steps=S, perturb=True)
     loss = ((out["depth_lidar"] - 0.3).abs().sum() + ((out["image_lidar"] - 0.5) ** 2).sum()) / N
-    loss.backward()
+    if dp and overlapped: dp.final_backward(loss)      # hash-table bucket reduced on a side stream behind the kernels' event
+    else: loss.backward()
     if dp: dp.allreduce_grads()
     return {{k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}}
 for fp16 in (False, True):
@@ -40,6 +41,9 @@ for fp16 in (False, True):
     g_1 = grads(m, None)                      # every rank also computes the whole batch alone
     worst = max(rel_err(g_dp[k], g_1[k]) for k in g_1)
     assert worst < 1e-4, (fp16, worst)
+    g_ov = grads(m, RayShardedDP(m, world_size=world, rank=rank), overlapped=True)
+    worst_ov = max(rel_err(g_ov[k], g_1[k]) for k in g_1)
+    assert worst_ov < 1e-4, ("overlapped", fp16, worst_ov)
     if rank == 0: print(f"mlp_fp16={{fp16}} sharded-vs-single worst rel err {{worst:.2e}}", flush=True)
 dist.barrier(); dist.destroy_process_group()
 '''
