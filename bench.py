@@ -53,7 +53,7 @@ def parse():
                     help="infer: BASELINE.json configs[3], forward-only render of one 64x2048 frame per step")
     ap.add_argument("--eager-rays", type=int, default=1024,
                     help="rays per step of the GPU-eager baseline leg (the reference's op graph in plain torch under fp16 autocast); 0 = skip")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=1,
                     help="CUDA streams the ray chunks of a step alternate over: the latency-bound tensor-core kernels of one chunk "
                          "overlap the L1TEX/LSU-bound gather / scatter kernels of the next (1 = serial)")
     ap.add_argument("--pipeline", default="split", choices=["split", "fused"])
@@ -275,18 +275,11 @@ def workload_config(args, note=None):
 # =============================================================================
 # GPU arm
 # =============================================================================
-def sector_counts(cfg):
-    """Algorithmic 32-byte sector requests per sample of the gather-type kernels (every divergent gather touches one
-    sector: 8 B static-hash corner, 16 B dynamic-hash slice pair / flow corner, 32 B plane texel) and vector reductions
-    (RED.E.ADD.F32x4 lane-ops) of the scatter-type kernels.  DESIGN.md 4.3."""
+def red_counts(cfg):
+    """Vector reductions (RED.E.ADD.F32x4 lane-ops) per sample of the kernels whose ceiling is the L2 atomic unit
+    (one per hash corner; DESIGN.md 4.2 'atomic floor')."""
     L = cfg.n_levels_hash
-    planes_s, planes_d = 4 * 3 * 4, 3 * (4 * 3 * 4)
-    return {
-        "k_fwd_gather": {"unit": "sectors", "per_sample": L * 8 + 3 * 3 * L * 4 + planes_s + planes_d},
-        "k_fwd_flow_tc": {"unit": "sectors", "per_sample": 8 * 8},
-        "k_bwd_scatter_static": {"unit": "red128", "per_sample": L * 8},
-        "k_bwd_flowgrid": {"unit": "red128", "per_sample": 8 * 8 * 0.5},
-    }
+    return {"k_bwd_scatter_static": L * 8}
 
 
 def micro_peaks():
@@ -541,27 +534,29 @@ def run_b200(args):
     peak, peak_src = peaks()
     samples_per_launch = min(rb, n_rays) * S_STEPS if not infer else min(model.infer_ray_chunk, n_rays) * S_STEPS
     kbytes = kernel_bytes(model.cfg)
-    secs = sector_counts(model.cfg)
+    reds = red_counts(model.cfg)
     mp = micro_peaks()
-    nb = ncu_binding().get("kernels", {})
+    nb = ncu_binding()
+    nbk = nb.get("kernels", {})
     kern = {}
     for name, ts in ktimes.items():
         avg = float(np.mean(ts))
         b = kbytes.get(name.replace("_tc", ""), None)
         k = {"avg_ms": avg, "launches_timed": len(ts), "alg_bytes_per_sample": b,
              "alg_gbs_l2_resident_not_a_dram_bound": (b * samples_per_launch / (avg * 1e-3) / 1e9) if b else None}
-        if name in secs:
-            u = secs[name]
-            rate = u["per_sample"] * samples_per_launch / (avg * 1e-3) / 1e9
-            ceil = mp.get("gather_gsectors_s" if u["unit"] == "sectors" else "red128_glaneops_s")
-            k["binding"] = {"unit": "G 32B-sector gathers/s (L2-resident, divergent)" if u["unit"] == "sectors" else "G RED.128 lane-ops/s (L2-resident)",
-                            "per_sample": u["per_sample"], "achieved": rate, "peak": ceil, "frac": (rate / ceil) if ceil else None}
-        if name in nb:
-            k["ncu"] = nb[name]            # pipe utilisation of this kernel from the committed ncu capture (profiles/)
+        if name in reds and mp.get("red128_glaneops_s"):
+            rate = reds[name] * samples_per_launch / (avg * 1e-3) / 1e9
+            k["binding"] = {"unit": "L2 atomic unit: G RED.128 lane-ops/s", "achieved": rate, "peak": mp["red128_glaneops_s"],
+                            "frac": rate / mp["red128_glaneops_s"], "source": "live duration x algorithmic REDs vs scripts/micro/red_bench.cu (profiles/r02_micro_peaks.json)"}
+        elif name in nbk and nbk[name].get("limiter_pct") is not None:
+            k["binding"] = {"unit": nbk[name]["limiter_unit"], "frac": nbk[name]["limiter_pct"] / 100.0, "achieved": None, "peak": None,
+                            "source": f"ncu --set full capture of this kernel ({nb.get('source')}): the profiler's own achieved/peak ratio of the busiest unit"}
+        if name in nbk:
+            k["ncu"] = nbk[name]
         kern[name] = k
     dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
     traffic = None
-    try:        # dram__bytes_read+write of the dominant kernel from the committed ncu capture (same launch shape only)
+    try:        # dram__bytes_read+write of the dominant kernel from the committed ncu capture (scaled to this launch size)
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         if args.levels == 16 and tj["dram_bytes_per_launch"].get(dom) is not None:
             traffic = tj["dram_bytes_per_launch"][dom] * (samples_per_launch / (float(tj.get("rays_per_launch", 8192)) * S_STEPS))
@@ -570,25 +565,19 @@ def run_b200(args):
     roofline = None
     if dom:
         kd = kern[dom]
-        bind = kd.get("binding")
+        bind = kd.get("binding") or {}
         alg = kd["alg_gbs_l2_resident_not_a_dram_bound"]
         dram_gbs = (traffic / (kd["avg_ms"] * 1e-3) / 1e9) if traffic else None
-        if bind and bind["frac"] is not None:
-            # the unit that binds the dominant kernel, in GB/s of 32-byte sectors (gathers) or 16-byte vector reductions
-            w = 32.0 if "sector" in bind["unit"] else 16.0
-            roofline = {"bound": bind["unit"], "kernel": dom, "achieved": bind["achieved"] * w, "peak": bind["peak"] * w,
-                        "unit": "GB/s", "frac": bind["frac"], "traffic": traffic,
-                        "peak_source": "measured: scripts/micro/*_bench.cu on this pool's B200 (profiles/r02_micro_peaks.json)"}
-        else:
-            roofline = {"bound": "hbm", "kernel": dom, "achieved": dram_gbs, "peak": peak, "unit": "GB/s",
-                        "frac": (dram_gbs / peak) if dram_gbs else None, "traffic": traffic, "peak_source": peak_src,
-                        "achieved_is": "MEASURED dram bytes (ncu) / live duration: this kernel is bound by " +
-                                       str((kd.get("ncu") or {}).get("limiter", "on-chip units (profiles/*_ncu_summary.md)"))}
-        roofline.update({
-            "hbm": {"measured_dram_gbs": dram_gbs, "peak": peak, "frac": (dram_gbs / peak) if dram_gbs else None, "peak_source": peak_src,
-                    "algorithmic_gbs": alg, "note": "algorithmic bytes (SURVEY 8(d)) / duration; the fp16 tables and live gradient slabs "
-                                                    "are L2-resident, so this is NOT a DRAM bound and may exceed the HBM peak"},
-            "kernels": kern})
+        # `bound` names the unit that binds the dominant kernel and `frac` is achieved/peak of THAT unit; the HBM view
+        # (measured DRAM bytes and the algorithmic-bytes figure of SURVEY 8(d)) sits beside it under "hbm"
+        roofline = {"bound": bind.get("unit", "hbm"), "kernel": dom, "achieved": bind.get("achieved"), "peak": bind.get("peak"),
+                    "unit": "fraction of the binding unit's peak" if bind.get("achieved") is None else "G lane-ops/s",
+                    "frac": bind.get("frac"), "traffic": traffic, "source": bind.get("source"),
+                    "hbm": {"bound": "hbm", "measured_dram_gbs": dram_gbs, "peak": peak, "unit": "GB/s",
+                            "frac": (dram_gbs / peak) if dram_gbs else None, "peak_source": peak_src, "algorithmic_gbs": alg,
+                            "note": "algorithmic bytes (SURVEY 8(d)) / duration: the fp16 tables and the live gradient slabs are L2-resident, "
+                                    "so this is NOT a DRAM bound and may exceed the HBM peak; measured_dram_gbs = ncu dram bytes / live duration"},
+                    "kernels": kern}
     total_rays = global_rays * args.steps
     value = total_rays / (ms * 1e-3)
     metric = ("inference rays/sec at 64x2048 rays x 768 samples" if infer else "training rays/sec at 64x1024 rays x 768 samples")

@@ -426,7 +426,7 @@ class OracleLiDAR4D(nn.Module):
         drop = torch.sigmoid(fused_mlp(inp, self.p("raydrop_net.params"), c.attr_in_dim, 1, 64, 2, self.mlp_dtype))
         h = torch.cat([drop, inten], -1)
         if mask is not None:
-            out[mask] = h
+            out[mask] = h.to(out.dtype)                    # lidar4d.py:219 (fp16 under autocast -> the fp32 output)
             return out
         return h
 
