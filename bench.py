@@ -383,6 +383,12 @@ def run_b200(args):
     for k in range(min(N_FRAMES, args.warmup + args.steps + 1)):
         fid = (k if strong else k * world + rank) % N_FRAMES
         ro, rd, t = synthetic_sweep(fid, N_FRAMES, H_SWEEP, W_frame)
+        if args.rays < ro.shape[0]:
+            # a batch smaller than the sweep is a RANDOM pixel subset, as the reference's loader draws it
+            # (base_dataset.py:71 torch.randint over H*W; kitti360_dataset.py:159-166) - not the first rows of the sweep,
+            # whose rays share one elevation and pile their plane-gradient reductions onto a few texels
+            sel = np.random.default_rng(1000 + fid).permutation(ro.shape[0])[:args.rays]
+            ro, rd = ro[sel], rd[sel]
         ro, rd = ro[lo:hi] if strong else ro[:n_rays], rd[lo:hi] if strong else rd[:n_rays]
         frames.append((torch.from_numpy(np.ascontiguousarray(ro)).pin_memory(), torch.from_numpy(np.ascontiguousarray(rd)).pin_memory(), float(t)))
     host_out = torch.empty(n_rays, 3).pin_memory()
