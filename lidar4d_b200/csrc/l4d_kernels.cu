@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "l4d_bwd.cuh"
@@ -998,20 +999,31 @@ static int check_rays(const L4DRays* r) {
 // CTA per SM although registers / shared memory / the 128 TMEM columns they actually allocate allow more
 template <typename K>
 static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid, int force_per_sm = 0) {
+  // the attribute / occupancy calls cost ~10 us of host time each: remember the answer per (kernel, smem, threads) -
+  // at the reference's 1,024-ray step the 15 launches of a step are otherwise host-bound
+  struct Memo { const void* k; size_t smem; int nt, force, per_sm; };
+  static thread_local Memo memo[64];
+  static thread_local int n_memo = 0;
   int per_sm = 0;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
-  if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
-  if (per_sm < 1) per_sm = 1;
-  if (force_per_sm > 0) per_sm = force_per_sm;
-  // small-shared-memory kernels: ask for just the carve-out the resident CTAs need, the rest stays L1 (the driver's
-  // default for k_fwd_gather was 132 KB of shared memory for 55 KB of use, i.e. half of the L1 given away)
-  if (smem <= 16 * 1024) {
-    const size_t need = (size_t)per_sm * (smem + 1024);
-    int pct = (int)((need * 100 + 233471) / 233472);
-    if (pct > 100) pct = 100;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < n_memo; ++i)
+    if (memo[i].k == key && memo[i].smem == smem && memo[i].nt == nt && memo[i].force == force_per_sm) { per_sm = memo[i].per_sm; break; }
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
+    if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
+    if (per_sm < 1) per_sm = 1;
+    if (force_per_sm > 0) per_sm = force_per_sm;
+    // small-shared-memory kernels: ask for just the carve-out the resident CTAs need, the rest stays L1 (the driver's
+    // default for k_fwd_gather was 132 KB of shared memory for 55 KB of use, i.e. half of the L1 given away)
+    if (smem <= 16 * 1024) {
+      const size_t need = (size_t)per_sm * (smem + 1024);
+      int pct = (int)((need * 100 + 233471) / 233472);
+      if (pct > 100) pct = 100;
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    if (n_memo < 64) memo[n_memo++] = Memo{key, smem, nt, force_per_sm, per_sm};
   }
   long g = (long)per_sm * sm_count();
   if ((long)work < g) g = work;
@@ -1180,6 +1192,10 @@ extern "C" int l4d_render_backward_ex(const L4DConfig* cfg, const void* staged, 
       int grid;
       rc = grid_for(k_bwd_scatter<L4D_NT>, L4D_NT, 0, tiles, grid);
       if (rc != L4D_OK) return rc;
+      {   // developer knob for A/B runs: L4D_SCATTER_GRID=0 -> one CTA per tile (hardware-balanced), N>0 -> N x the persistent grid
+        static const char* e = getenv("L4D_SCATTER_GRID");
+        if (e) { const int m = atoi(e); grid = m <= 0 ? (int)tiles : (int)((long)grid * m < (long)tiles ? (long)grid * m : (long)tiles); }
+      }
       ++g_launches; k_bwd_scatter<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
       prof_mark(st, "k_bwd_scatter");
       rc = grid_for(k_bwd_scatter_static<L4D_NT>, L4D_NT, 0, tiles, grid);

@@ -31,40 +31,52 @@ class Adam(torch.optim.Optimizer):
         self._exp_avg_sq = None
         self._step = 0
         self._arena_id = None
+        self._seg_cache = None
 
     # ---- arena bookkeeping ---------------------------------------------------------------------------------------
     def _segments(self):
-        """One Adam segment per hash table (they emit their fp16 copies), the other tensors merged per lr."""
+        """One Adam segment per hash table (they emit their fp16 copies), the other tensors merged per lr.  The segment
+        STRUCTURE is cached per (arena, equality pattern of the group learning rates); a scheduler that rescales the
+        rates only rewrites the lr fields."""
         eng = self._eng
         ts = eng.tensors()
         eng.ensure_flat(ts)
-        by_ptr = {t.data_ptr(): n for n, t in ts.items()}
-        lr_of = {}
-        for g in self.param_groups:
+        lrs = [float(g["lr"]) for g in self.param_groups]
+        key = (id(eng.flat_p), tuple(lrs.index(l) for l in lrs))
+        if self._seg_cache is not None and self._seg_cache[0] == key:
+            _, arr, n, owner = self._seg_cache
+            for i in range(n):
+                arr[i].lr = lrs[owner[i]]
+            return arr, n
+        by_ptr = {t.data_ptr(): nme for nme, t in ts.items()}
+        group_of = {}
+        for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
                 if p.numel() == 0:
                     continue
-                n = by_ptr.get(p.data_ptr())
-                if n is None:
+                nme = by_ptr.get(p.data_ptr())
+                if nme is None:
                     raise ValueError("lidar4d_b200.optim.Adam only updates the hot-path parameters of its model "
                                      "(use torch.optim.Adam for the others, e.g. the U-Net)")
-                lr_of[n] = float(g["lr"])
-        segs = []
-        for n in eng.names:                                   # arena order
-            if n not in lr_of:
+                group_of[nme] = gi
+        segs = []                                             # [begin, end, group index, is_table]
+        for nme in eng.names:                                 # arena order
+            if nme not in group_of:
                 continue
-            o, k = eng.offsets[n]
-            table = ("hash" in n) or n.endswith("grid_enc.params")
+            o, k = eng.offsets[nme]
+            table = ("hash" in nme) or nme.endswith("grid_enc.params")
             end = o + (k + 3) // 4 * 4
-            if segs and not table and not segs[-1][3] and segs[-1][2] == lr_of[n]:
-                segs[-1] = (segs[-1][0], end, lr_of[n], False)
+            gi = group_of[nme]
+            if segs and not table and not segs[-1][3] and lrs[segs[-1][2]] == lrs[gi]:
+                segs[-1][1] = end
             else:
-                segs.append((o, end, lr_of[n], table))
+                segs.append([o, end, gi, table])
         if len(segs) > _capi.ADAM_MAX_SEGMENTS:
             raise ValueError("too many Adam segments")
         arr = (_capi.L4DAdamGroup * len(segs))()
-        for i, (b, e, lr, _) in enumerate(segs):
-            arr[i].begin, arr[i].end, arr[i].lr = b, e, lr
+        for i, (b, e, gi, _) in enumerate(segs):
+            arr[i].begin, arr[i].end, arr[i].lr = b, e, lrs[gi]
+        self._seg_cache = (key, arr, len(segs), [sg[2] for sg in segs])
         return arr, len(segs)
 
     @torch.no_grad()

@@ -288,6 +288,24 @@ def rays_case():
     print(f"wrote {p}")
 
 
+def unet_case():
+    """tests/golden/unet.npz: the reference's own UNet (model/unet.py, imported unchanged) in eval mode on a small
+    panorama, parameters from parity_util.fill_state_dict (regenerated, not stored)."""
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from model.unet import UNet
+    from parity_util import fill_state_dict
+    net = fill_state_dict(UNet(in_channels=3, out_channels=1)).eval()
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 3, 34, 70, generator=g)
+    with torch.no_grad():
+        y = net(x)
+    keys = sorted(net.state_dict().keys())
+    p = os.path.join(ROOT, "tests", "golden", "unet.npz")
+    np.savez_compressed(p, x=x.numpy(), y=y.numpy(), keys=np.array(keys), shapes=np.array([str(tuple(net.state_dict()[k].shape)) for k in keys]))
+    print(f"wrote {p}: out mean {float(y.mean()):.6f}")
+
+
 def trainer_case(seed=31):
     """tests/golden/trainer_step.npz: loss / predictions of the UNMODIFIED Trainer.train_step and eval_step
     (model/runner.py:166-434, flow loss on) on the reference model-on-shim, for tests/test_trainer_dropin.py."""
@@ -332,10 +350,12 @@ if __name__ == "__main__":
     if "--trainer-only" in sys.argv:
         trainer_case()
         rays_case()
+        unet_case()
         sys.exit(0)
     hash_index_vectors()
     trainer_case()
     rays_case()
+    unet_case()
     # interior frame (both neighbours), perturb off
     run_case("ref_small_interior", time=0.4, n_rays_hw=(4, 12), num_steps=48, perturb=False, seed=3)
     # first frame (no backward neighbour), slice index integral (t*7 == 0)

@@ -107,3 +107,22 @@ def grad_errors(a, b, tol: float = 1e-4):
     d = (a - b).abs()
     bmax = float(b.abs().max()) + 1e-30
     return float(d.max() / bmax), float(d.norm() / (b.norm() + 1e-30)), float((d > tol * bmax).double().mean())
+
+
+def fill_state_dict(module, scale: float = 0.2):
+    """Deterministic, storage-free parameters for fixtures of library modules: every tensor is a smooth function of its
+    flat index and of its key (positive for variances), identical for any implementation with the same state_dict."""
+    import zlib
+    with torch.no_grad():
+        for k, v in module.state_dict().items():
+            if not v.dtype.is_floating_point:
+                continue
+            ph = (zlib.crc32(k.encode()) % 1000) * 0.01
+            i = torch.arange(v.numel(), dtype=torch.float64)
+            x = torch.cos(i * 0.7548776662 + ph) * scale
+            if k.endswith("running_var"):
+                x = x.abs() + 0.5
+            elif k.endswith(".weight") and v.dim() == 1:      # norm scales around 1
+                x = 1.0 + x
+            v.copy_(x.view(v.shape).to(v.dtype))
+    return module
