@@ -166,11 +166,19 @@ def peaks():
 # =============================================================================
 # CPU arm: the oracle port of the reference python path
 # =============================================================================
+def reference_main_loss(out):
+    """runner.py:193-213 with the default criteria and weights (main_lidar4d.py:63-72,88) against the bench's synthetic
+    ground truth (no ray dropped, intensity 0.5, depth 0.3), as a torch op chain - what the baseline legs time; the CUDA arm
+    evaluates the same expression with lidar4d_b200.losses.lidar_main_loss."""
+    img = out["image_lidar"]
+    return (1.0 * (out["depth_lidar"] - 0.3).abs() + 0.01 * (img[..., 0] - 0.8) ** 2 + 0.1 * (img[..., 1] - 0.5) ** 2).mean()
+
+
 def cpu_reference_step(orc, opt, ro, rd, t, seed):
     from oracle import lidar4d_oracle as O  # noqa: F401  (bench cpu_baseline / --impl reference leg only)
     opt.zero_grad()
     out = orc.render(torch.from_numpy(ro), torch.from_numpy(rd), t, num_steps=S_STEPS, perturb=True, seed=seed)
-    loss = (out["depth_lidar"] - 0.3).abs().mean() + ((out["image_lidar"] - 0.5) ** 2).mean()
+    loss = reference_main_loss(out)
     loss.backward()
     opt.step()
     return float(loss)
@@ -315,7 +323,7 @@ def gpu_eager_baseline(levels, n_rays, dev):
             opt.zero_grad()
             with torch.autocast("cuda", dtype=torch.float16):
                 out = orc.render(ro_t, rd_t, float(t), num_steps=S_STEPS, perturb=True, seed=seed)
-                loss = (out["depth_lidar"] - 0.3).abs().mean() + ((out["image_lidar"] - 0.5) ** 2).mean()
+                loss = reference_main_loss(out)
             scaler.scale(loss).backward()
             scaler.step(opt)
             scaler.update()
@@ -392,6 +400,8 @@ def run_b200(args):
         ro, rd = ro[lo:hi] if strong else ro[:n_rays], rd[lo:hi] if strong else rd[:n_rays]
         frames.append((torch.from_numpy(np.ascontiguousarray(ro)).pin_memory(), torch.from_numpy(np.ascontiguousarray(rd)).pin_memory(), float(t)))
     host_out = torch.empty(n_rays, 3).pin_memory()
+    from lidar4d_b200.losses import lidar_main_loss
+    gt_d = torch.tensor([1.0, 0.5, 0.3], device=dev).repeat(n_rays, 1)      # (no drop, intensity 0.5, depth 0.3) for every ray
     ray_off0 = lo if strong else rank * n_rays
 
     def inputs(i, e2e):
@@ -409,7 +419,9 @@ def run_b200(args):
     def chunk(h, ro_d, rd_d, t, e2e, last):
         out = model.render(ro_d[None, h:h + rb], rd_d[None, h:h + rb], t, staged=False, num_steps=S_STEPS,
                            perturb=True, ray_offset=ray_off0 + h)
-        loss = ((out["depth_lidar"] - 0.3).abs().sum() + ((out["image_lidar"] - 0.5) ** 2).sum()) / global_rays
+        # the reference's main loss (runner.py:193-213: L1 depth, label-smoothed ray-drop MSE, intensity MSE, defaults of
+        # main_lidar4d.py:70-72,88) against a synthetic ground-truth image, value + gradient in one launch
+        loss = lidar_main_loss(out["depth_lidar"], out["image_lidar"], gt_d[None, h:h + rb], 1.0, 0.01, 0.1, 0.2) * (1.0 / global_rays)
         if last:
             dp.final_backward(loss)          # the hash-table bucket starts reducing while the flow backward still runs
         else:

@@ -123,9 +123,9 @@ class _Engine:
     * the persistent gradient work buffer (zero between launches: the fold kernels clear what they consume).
     """
 
-    def __init__(self, owner: "LiDAR4D"):
+    def __init__(self, owner: "LiDAR4D", cfg=None):
         self.owner = owner
-        self.cfg = owner.cfg
+        self.cfg = cfg if cfg is not None else owner.cfg
         # default = what the reference does: tiny-cuda-nn's FullyFusedMLP consumes fp16 copies of its fp32 parameters;
         # this is also the mode that runs the dense kernels on the tcgen05 tensor cores
         self.mlp_fp16 = True
@@ -148,6 +148,17 @@ class _Engine:
         self._gtab = None
         self.hash_grads_hook = None  # (torch.cuda.Event, callable): see parallel.RayShardedDP.final_backward
         self.timing = None         # {'fwd': [(ev0, ev1)], 'bwd': [...]}: CUDA events around the fused kernels
+
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(model) (some EMA / checkpoint helpers do this): the copy gets a FRESH engine - ctypes pointer
+        tables cannot be copied and its arenas are rebuilt lazily around the copied parameters on first use."""
+        owner = memo.get(id(self.owner), self.owner)
+        new = _Engine.__new__(_Engine)
+        memo[id(self)] = new
+        _Engine.__init__(new, owner, cfg=self.cfg)       # (the owner's own attributes are still being copied at this point)
+        new.set_mlp_fp16(self.mlp_fp16)
+        new.static_params = self.static_params
+        return new
 
     def set_mlp_fp16(self, on: bool):
         if bool(on) != self.mlp_fp16:

@@ -120,6 +120,8 @@ def fill_state_dict(module, scale: float = 0.2):
             ph = (zlib.crc32(k.encode()) % 1000) * 0.01
             i = torch.arange(v.numel(), dtype=torch.float64)
             x = torch.cos(i * 0.7548776662 + ph) * scale
+            if v.dim() >= 2:                                    # conv / linear weights: keep activations O(1) through deep stacks
+                x = x * (1.4 / scale) / float(v[0].numel()) ** 0.5
             if k.endswith("running_var"):
                 x = x.abs() + 0.5
             elif k.endswith(".weight") and v.dim() == 1:      # norm scales around 1

@@ -142,7 +142,11 @@ def test_fused_adam_matches_torch_adam(dev):
         m1._jitter_calls = m2._jitter_calls
     for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
         if a.numel():
-            assert rel_err(b, a) < 2e-5, n
+            # Adam's first steps move an entry by ~lr * sign(g): an entry whose gradient is pure summation noise of the
+            # atomics (a 1e-7 event per entry) may legitimately differ by 2 lr between two runs - allow a 1e-4 fraction
+            d = (a.detach() - b.detach()).abs()
+            bad = float((d > 2e-5 * float(a.detach().abs().max())).float().mean())
+            assert bad <= 1e-4, (n, bad, rel_err(b, a))
     # the working set the kernels read after the fused step == a from-scratch staging of the same parameters
     with torch.no_grad():
         x = _render(m2, dev)["depth_lidar"].clone()
@@ -179,6 +183,21 @@ def test_checkpoint_round_trip(dev):
     with torch.no_grad():
         a, b = _render(m, dev)["depth_lidar"], _render(m2, dev)["depth_lidar"]
     assert torch.equal(a, b) and not torch.equal(before, b)
+
+
+def test_deepcopy_gives_an_independent_working_model(dev):
+    orc, m = _model()
+    _loss(_render(m, dev)).backward()                  # arenas, pointer tables and .grad views exist
+    m2 = copy.deepcopy(m)
+    assert m2._engine is not m._engine and m2._engine.owner is m2
+    with torch.no_grad():
+        a, b = _render(m, dev)["depth_lidar"], _render(m2, dev)["depth_lidar"]
+        assert torch.equal(a, b)
+        for p in m2.sigma_net.parameters():
+            p.mul_(0.5)
+        c, d = _render(m, dev)["depth_lidar"], _render(m2, dev)["depth_lidar"]
+    assert torch.equal(a, c) and not torch.allclose(a, d)
+    assert m2.sigma_net.params.data_ptr() != m.sigma_net.params.data_ptr()
 
 
 def test_launch_counter_counts_kernels(dev):

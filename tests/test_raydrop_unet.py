@@ -25,7 +25,7 @@ def test_state_dict_surface_and_function_match_reference_unet():
     with torch.no_grad():
         y = net(torch.from_numpy(fx["x"]))
     assert y.shape == fx["y"].shape
-    assert rel_err(y, fx["y"]) < 5e-4          # fused SDPA vs the explicit softmax, fp32 (activations reach O(100) with these weights)
+    assert rel_err(y, fx["y"]) < 1e-5
 
 
 def test_lidar4d_accepts_it_and_keeps_the_unet_keys():
@@ -57,8 +57,8 @@ def test_unet_gpu_fp32_and_bf16():
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     e32, e16 = rel_err(y, fx["y"]), rel_err(yb.float(), fx["y"])
-    assert e32 < 1e-3, e32
-    assert torch.isfinite(yb).all() and e16 < 0.15, e16      # bf16 through 23 layers with O(100) activations (synthetic weights)
+    assert e32 < 1e-4, e32
+    assert torch.isfinite(yb).all() and e16 < 5e-2, e16      # bf16 through 23 layers
     # training mode: attention dropout mask + BN batch statistics run and give gradients to every parameter
     net.train()
     out = net(torch.rand(2, 3, 66, 130, device=dev))
