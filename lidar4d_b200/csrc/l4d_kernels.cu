@@ -1002,16 +1002,28 @@ static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid, int
   // the attribute / occupancy calls cost ~10 us of host time each: remember the answer per (kernel, smem, threads) -
   // at the reference's 1,024-ray step the 15 launches of a step are otherwise host-bound
   struct Memo { const void* k; size_t smem; int nt, force, per_sm; };
+  struct SmemSet { const void* k; size_t max_set; };
   static thread_local Memo memo[64];
-  static thread_local int n_memo = 0;
+  static thread_local SmemSet smem_set[32];
+  static thread_local int n_memo = 0, n_set = 0;
   int per_sm = 0;
   const void* key = reinterpret_cast<const void*>(kernel);
+  // the opt-in dynamic shared-memory limit is a sticky per-function attribute: only ever RAISE it (configurations with
+  // different tile sizes alternate in one process, and lowering it would make the larger one's next launch invalid)
+  {
+    SmemSet* e = nullptr;
+    for (int i = 0; i < n_set; ++i) if (smem_set[i].k == key) { e = &smem_set[i]; break; }
+    if (!e || smem > e->max_set) {
+      cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err != cudaSuccess) return l4d_fail(L4D_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+      if (e) e->max_set = smem;
+      else if (n_set < 32) smem_set[n_set++] = SmemSet{key, smem};
+    }
+  }
   for (int i = 0; i < n_memo; ++i)
     if (memo[i].k == key && memo[i].smem == smem && memo[i].nt == nt && memo[i].force == force_per_sm) { per_sm = memo[i].per_sm; break; }
   if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
     if (e != cudaSuccess) return l4d_fail(L4D_ECUDA, "occupancy query: %s", cudaGetErrorString(e));
     if (per_sm < 1) per_sm = 1;
     if (force_per_sm > 0) per_sm = force_per_sm;

@@ -109,6 +109,28 @@ def grad_errors(a, b, tol: float = 1e-4):
     return float(d.max() / bmax), float(d.norm() / (b.norm() + 1e-30)), float((d > tol * bmax).double().mean())
 
 
+def relu_margin_all(oracle, stages, rays_d) -> float:
+    """relu_margin() plus the four hidden layers of the two attribute heads (lidar4d.py:191-223) on the samples inside
+    the attribute mask: the smallest |pre-activation| of EVERY ReLU of the network for this input."""
+    from oracle import lidar4d_oracle as O
+    c = oracle.cfg
+    m = relu_margin(oracle, stages)
+    with torch.no_grad():
+        mask = stages["mask"].reshape(-1)
+        if bool(mask.any()):
+            N, S = stages["weights"].shape
+            d = torch.as_tensor(rays_d).float().view(N, 1, 3).expand(N, S, 3).reshape(-1, 3)[mask]
+            enc = O.frequency_encode((d + 1) / 2, c.view_degree)
+            inp = torch.cat([enc, stages["geo_feat"].float()[mask]], -1)
+            inp = torch.cat([inp, torch.ones(inp.shape[0], c.attr_in_pad - c.attr_in_dim)], -1)
+            for net in ("intensity_net.params", "raydrop_net.params"):
+                W1, W2, _ = O.mlp_layers(oracle.p(net).float(), c.attr_in_pad, 64, 2)
+                y1 = inp @ W1.t()
+                y2 = torch.relu(y1) @ W2.t()
+                m = min(m, float(y1.abs().min()), float(y2.abs().min()))
+    return m
+
+
 def fill_state_dict(module, scale: float = 0.2):
     """Deterministic, storage-free parameters for fixtures of library modules: every tensor is a smooth function of its
     flat index and of its key (positive for variances), identical for any implementation with the same state_dict."""

@@ -93,10 +93,12 @@ def test_render_forward_backward(dev, t, S, perturb, seed, surface, pipeline):
     assert not bad, f"worst {max(errs.values()):.2e}; failing: {bad}"
 
 
-@pytest.mark.parametrize("name", ["ref_small_interior", "ref_small_first", "ref_small_last"])
+@pytest.mark.parametrize("name", ["ref_small_interior", "ref_small_first", "ref_small_last", "ref_small_active"])
 def test_against_reference_golden(dev, name):
+    import ast
     fx = np.load(os.path.join(GOLD, name + ".npz"))
-    orc = O.build_seeded(small_config(), int(fx["seed"]), flow_last_std=0.02)
+    extra = ast.literal_eval(str(fx["extra"])) if "extra" in fx.files else {}    # active_sensor / density_scale / bound of the case
+    orc = O.build_seeded(small_config(**extra), int(fx["seed"]), flow_last_std=0.02)
     m = cuda_model_from_oracle(orc)
     m.jitter_seed = int(fx["seed"])
     S = int(fx["num_steps"])
@@ -118,6 +120,32 @@ def test_against_reference_golden(dev, name):
             assert n_ref == 0.0, k
             continue
         assert abs(float(got[k].double().norm()) - n_ref) <= 1e-4 * n_ref + 1e-12, k
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_renderer_options_against_oracle(dev, mode):
+    """active_sensor (exponent x2, renderer.py:100-102), density_scale and a non-unit bound, both kernel families."""
+    from parity_util import relu_margin_all
+    ro, rd = _rays(3, 8)
+    N, S = ro.shape[0], 150
+    for seed in range(12, 60):          # first seed with every ReLU (attribute heads included) clear of its kink
+        orc = O.build_seeded(small_config(active_sensor=True, density_scale=0.7, bound=1.5), seed, flow_last_std=0.02)
+        if mode == "tc":
+            orc.mlp_dtype = "fp16"
+        ref = orc.render(torch.from_numpy(ro), torch.from_numpy(rd), 0.4, num_steps=S, perturb=True, seed=seed, return_stages=True)
+        if relu_margin_all(orc, ref, rd) > 3e-7:
+            break
+    m = cuda_model_from_oracle(orc).set_mlp_fp16(mode == "tc")
+    m.jitter_seed = seed
+    out = m.render(torch.from_numpy(ro)[None].to(dev), torch.from_numpy(rd)[None].to(dev), torch.tensor([[0.4]]), num_steps=S, perturb=True)
+    for k in ("depth_lidar", "image_lidar", "weights"):
+        assert rel_err(out[k], ref[k]) < TOL, k
+    (ref["depth_lidar"].sum() + ref["image_lidar"].sum()).backward()
+    (out["depth_lidar"].sum() + out["image_lidar"].sum()).backward()
+    og = orc.ref_named_grads()
+    errs = {k: rel_err(p.grad, og[k]) for k, p in m.named_parameters() if p.grad is not None and og[k].numel()}
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
 
 
 def test_flow_forward_backward(dev):

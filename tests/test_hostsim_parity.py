@@ -99,10 +99,12 @@ def test_render_forward_backward(t, S, perturb, seed, surface):
     assert float(og["flow_net.mlp.0.weight"].abs().max()) > 0
 
 
-@pytest.mark.parametrize("name", ["ref_small_interior", "ref_small_first", "ref_small_last"])
+@pytest.mark.parametrize("name", ["ref_small_interior", "ref_small_first", "ref_small_last", "ref_small_active"])
 def test_against_reference_golden(name):
+    import ast
     fx = np.load(os.path.join(GOLD, name + ".npz"))
-    orc = O.build_seeded(small_config(), int(fx["seed"]), flow_last_std=0.02)
+    extra = ast.literal_eval(str(fx["extra"])) if "extra" in fx.files else {}    # active_sensor / density_scale / bound
+    orc = O.build_seeded(small_config(**extra), int(fx["seed"]), flow_last_std=0.02)
     hs = H.HostSim(orc)
     S = int(fx["num_steps"])
     got = hs.render(fx["rays_o"], fx["rays_d"], float(fx["time"]), S, perturb=bool(fx["perturb"]),

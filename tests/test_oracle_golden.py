@@ -11,7 +11,7 @@ from lidar4d_b200.geometry import FieldConfig
 from parity_util import small_config, rel_err, full_oracle
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CASES = ["ref_small_interior", "ref_small_first", "ref_small_last"]
+CASES = ["ref_small_interior", "ref_small_first", "ref_small_last", "ref_small_active"]
 
 
 def load(name):
@@ -25,7 +25,9 @@ def oracle_case(fx):
     if "levels" in fx.files:
         orc = full_oracle(int(fx["levels"]), int(fx["seed"]), bool(int(fx["smooth"])))
     else:
-        orc = O.build_seeded(small_config(), int(fx["seed"]), flow_last_std=0.02)
+        import ast
+        extra = ast.literal_eval(str(fx["extra"])) if "extra" in fx.files else {}      # renderer options of the case
+        orc = O.build_seeded(small_config(**extra), int(fx["seed"]), flow_last_std=0.02)
     chk = sum(float(v.double().sum()) for v in orc.ref_state_dict().values())
     assert abs(chk - float(fx["param_checksum"])) < 1e-6 * abs(float(fx["param_checksum"])), "seeded parameters drifted"
     return orc
