@@ -1020,7 +1020,8 @@ static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid, int
       else if (n_set < 32) smem_set[n_set++] = SmemSet{key, smem};
     }
   }
-  for (int i = 0; i < n_memo; ++i)
+  static const bool no_memo = getenv("L4D_NO_MEMO") != nullptr;      // developer A/B knob
+  for (int i = 0; i < n_memo && !no_memo; ++i)
     if (memo[i].k == key && memo[i].smem == smem && memo[i].nt == nt && memo[i].force == force_per_sm) { per_sm = memo[i].per_sm; break; }
   if (per_sm == 0) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
@@ -1035,7 +1036,7 @@ static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid, int
       if (pct > 100) pct = 100;
       cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
-    if (n_memo < 64) memo[n_memo++] = Memo{key, smem, nt, force_per_sm, per_sm};
+    if (n_memo < 64 && !no_memo) memo[n_memo++] = Memo{key, smem, nt, force_per_sm, per_sm};
   }
   long g = (long)per_sm * sm_count();
   if ((long)work < g) g = work;
