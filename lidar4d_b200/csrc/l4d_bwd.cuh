@@ -278,7 +278,13 @@ struct DfeatFromPlane {
 };
 
 // scatter dL/dfeature through the encoders of one sample at (x,y,z) with its flow; dflow[6] out
-template <bool WARP_AGG, class DF, bool STATIC_HASH = true>
+// PARTS: which sinks this instantiation serves (the split pipeline runs them as separate kernels so that each keeps
+// fewer values live: bit 0 static planes, bit 1 time planes (+ dL/dflow), bit 2 dynamic hash)
+#define L4D_SC_STATIC_PLANES 1
+#define L4D_SC_TIME_PLANES 2
+#define L4D_SC_DYNAMIC_HASH 4
+#define L4D_SC_ALL 7
+template <bool WARP_AGG, class DF, bool STATIC_HASH = true, int PARTS = L4D_SC_ALL>
 L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
                              const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6], bool active);
 
@@ -292,7 +298,7 @@ L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads&
 
 // WARP_AGG: every lane of the warp must call (lanes without a sample pass active=false and a
 // provider that returns 0; they take part in the plane aggregation with zero contributions)
-template <bool WARP_AGG, class DF, bool STATIC_HASH>
+template <bool WARP_AGG, class DF, bool STATIC_HASH, int PARTS>
 L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
                              const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6], bool active) {
 #pragma unroll
@@ -311,7 +317,7 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
   for (int sc = 0; sc < nS; ++sc) {
     const int R = (int)M.plane_res[sc];
     const int T = (int)M.time_res;
-    {   // static planes: product rule over (x,y) (x,z) (y,z)
+    if (PARTS & L4D_SC_STATIC_PLANES) {   // static planes: product rule over (x,y) (x,z) (y,z)
       float d[8], v0[8], v1[8], v2[8], dummy[8], g[8];
 #pragma unroll
       for (int c = 0; c < 8; c += 4) l4d_dfeat_fn.ld4(sc * 8 + c, *reinterpret_cast<float(*)[4]>(d + c));
@@ -329,7 +335,7 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
       for (int c = 0; c < 8; ++c) g[c] = d[c] * v0[c] * v1[c];
       l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][3], R, b2, g, false);
     }
-    {   // time planes (x,t) (y,t) (z,t): three queries, warped ones also feed d(coords) -> flow
+    if (PARTS & L4D_SC_TIME_PLANES) {   // time planes (x,t) (y,t) (z,t): three queries, warped ones also feed d(coords) -> flow
       float d[8];
 #pragma unroll
       for (int c = 0; c < 8; c += 4) l4d_dfeat_fn.ld4(row_plane_d + sc * 8 + c, *reinterpret_cast<float(*)[4]>(d + c));
@@ -379,7 +385,7 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
 
   // dynamic hash: only the (x,t) query carries gradient (lidar4d.py:160-161,169-170 are no_grad)
 #pragma unroll 1
-  for (int p = 0; p < 3; ++p) {
+  for (int p = 0; (PARTS & L4D_SC_DYNAMIC_HASH) && p < 3; ++p) {
     const float ca = p == 2 ? y : x, cb = p == 0 ? y : z;
     float* glo = G.hd[p][F.cur.slice_lo];
     float* ghi = G.hd[p][F.cur.slice_hi];

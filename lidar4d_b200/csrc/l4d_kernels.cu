@@ -1203,14 +1203,28 @@ extern "C" int l4d_render_backward_ex(const L4DConfig* cfg, const void* staged, 
     }
     {
       int grid;
-      rc = grid_for(k_bwd_scatter<L4D_NT>, L4D_NT, 0, tiles, grid);
-      if (rc != L4D_OK) return rc;
-      {   // developer knob for A/B runs: L4D_SCATTER_GRID=0 -> one CTA per tile (hardware-balanced), N>0 -> N x the persistent grid
-        static const char* e = getenv("L4D_SCATTER_GRID");
-        if (e) { const int m = atoi(e); grid = m <= 0 ? (int)tiles : (int)((long)grid * m < (long)tiles ? (long)grid * m : (long)tiles); }
+      {
+        // default: ONE kernel (its dynamic-hash reductions drain under the plane arithmetic).  L4D_SCATTER_SPLIT=1 (A/B knob)
+        // runs the time planes and the static planes + dynamic hash as two kernels at higher occupancy: measured slower,
+        // 17.1 + 12.7 ms vs 26.6 ms per 16,384 rays
+        static const char* e = getenv("L4D_SCATTER_SPLIT");
+        const bool split = e && atoi(e) != 0;
+        if (split) {
+          rc = grid_for(k_bwd_scatter<L4D_NT, L4D_SC_TIME_PLANES, L4D_SCATTER_T_CTAS>, L4D_NT, 0, tiles, grid);
+          if (rc != L4D_OK) return rc;
+          ++g_launches; k_bwd_scatter<L4D_NT, L4D_SC_TIME_PLANES, L4D_SCATTER_T_CTAS><<<grid, L4D_NT, 0, st>>>(A);
+          prof_mark(st, "k_bwd_scatter_time");
+          rc = grid_for(k_bwd_scatter<L4D_NT, L4D_SC_STATIC_PLANES | L4D_SC_DYNAMIC_HASH, L4D_SCATTER_S_CTAS>, L4D_NT, 0, tiles, grid);
+          if (rc != L4D_OK) return rc;
+          ++g_launches; k_bwd_scatter<L4D_NT, L4D_SC_STATIC_PLANES | L4D_SC_DYNAMIC_HASH, L4D_SCATTER_S_CTAS><<<grid, L4D_NT, 0, st>>>(A);
+          prof_mark(st, "k_bwd_scatter_sd");
+        } else {
+          rc = grid_for(k_bwd_scatter<L4D_NT, L4D_SC_ALL, L4D_SCATTER_MIN_CTAS>, L4D_NT, 0, tiles, grid);
+          if (rc != L4D_OK) return rc;
+          ++g_launches; k_bwd_scatter<L4D_NT, L4D_SC_ALL, L4D_SCATTER_MIN_CTAS><<<grid, L4D_NT, 0, st>>>(A);
+          prof_mark(st, "k_bwd_scatter");
+        }
       }
-      ++g_launches; k_bwd_scatter<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
-      prof_mark(st, "k_bwd_scatter");
       rc = grid_for(k_bwd_scatter_static<L4D_NT>, L4D_NT, 0, tiles, grid);
       if (rc != L4D_OK) return rc;
       ++g_launches; k_bwd_scatter_static<L4D_NT><<<grid, L4D_NT, 0, st>>>(A);
