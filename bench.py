@@ -584,7 +584,8 @@ def run_b200(args):
             k["binding"] = {"unit": "L2 atomic unit: G RED.128 lane-ops/s", "achieved": rate, "peak": mp["red128_glaneops_s"],
                             "frac": rate / mp["red128_glaneops_s"], "source": "live duration x algorithmic REDs vs scripts/micro/red_bench.cu (profiles/r02_micro_peaks.json)"}
         elif name in nbk and nbk[name].get("limiter_pct") is not None:
-            k["binding"] = {"unit": nbk[name]["limiter_unit"], "frac": nbk[name]["limiter_pct"] / 100.0, "achieved": None, "peak": None,
+            k["binding"] = {"unit": nbk[name]["limiter_unit"], "frac": nbk[name]["limiter_pct"] / 100.0,
+                            "achieved": nbk[name]["limiter_pct"], "peak": 100.0, "achieved_unit": "% of the unit's peak rate (ncu)",
                             "source": f"ncu --set full capture of this kernel ({nb.get('source')}): the profiler's own achieved/peak ratio of the busiest unit"}
         if name in nbk:
             k["ncu"] = nbk[name]
@@ -606,7 +607,7 @@ def run_b200(args):
         # `bound` names the unit that binds the dominant kernel and `frac` is achieved/peak of THAT unit; the HBM view
         # (measured DRAM bytes and the algorithmic-bytes figure of SURVEY 8(d)) sits beside it under "hbm"
         roofline = {"bound": bind.get("unit", "hbm"), "kernel": dom, "achieved": bind.get("achieved"), "peak": bind.get("peak"),
-                    "unit": "fraction of the binding unit's peak" if bind.get("achieved") is None else "G lane-ops/s",
+                    "unit": bind.get("achieved_unit", "G lane-ops/s"),
                     "frac": bind.get("frac"), "traffic": traffic, "source": bind.get("source"),
                     "hbm": {"bound": "hbm", "measured_dram_gbs": dram_gbs, "peak": peak, "unit": "GB/s",
                             "frac": (dram_gbs / peak) if dram_gbs else None, "peak_source": peak_src, "algorithmic_gbs": alg,
