@@ -174,9 +174,10 @@ L4D_HD void l4d_bw_sigma_c(const DevModel& M, const BwSample& s, const float* fe
 // is summed with a segmented warp scan and only its last lane issues the REDs.
 #if defined(__CUDACC__)
 struct WarpRuns {
-  int dist;     // lane - first lane of this lane's run of equal keys
-  int maxdist;  // longest run of the warp - 1 (warp-uniform): the scans stop after ceil(log2(maxdist+1)) steps
-  bool tail;    // last lane of its run
+  int dist;       // lane - first lane of this lane's run of equal keys
+  int maxdist;    // longest run of the warp - 1 (warp-uniform): the scans stop after ceil(log2(maxdist+1)) steps
+  bool tail;      // last lane of its run
+  unsigned mask;  // the lanes of this lane's run
 };
 __device__ __forceinline__ WarpRuns l4d_warp_runs(int key) {
   const unsigned lane = threadIdx.x & 31u;
@@ -185,9 +186,13 @@ __device__ __forceinline__ WarpRuns l4d_warp_runs(int key) {
   const unsigned heads = __ballot_sync(0xffffffffu, head);
   const unsigned below = heads & (0xffffffffu >> (31u - lane));
   WarpRuns r;
-  r.dist = (int)lane - (31 - __clz(below));
+  const int first = 31 - __clz(below);
+  r.dist = (int)lane - first;
   r.maxdist = (int)__reduce_max_sync(0xffffffffu, (unsigned)r.dist);
   r.tail = (lane == 31u) || ((heads >> (lane + 1u)) & 1u);
+  const unsigned above = lane == 31u ? 0u : (heads & (0xffffffffu << (lane + 1u)));      // heads of later runs
+  const int last = above ? (__ffs(above) - 2) : 31;                                         // last lane of this run
+  r.mask = (0xffffffffu >> (31 - last)) & (0xffffffffu << first);
   return r;
 }
 // inclusive segmented scans of 8 values at once (8 independent shuffles per step); the tail lane of a run ends up
@@ -204,6 +209,32 @@ __device__ __forceinline__ void l4d_seg_sum8(float (&v)[8], const WarpRuns& r) {
     }
   }
 }
+// (A/B option, measured 3.5x SLOWER than the scans - REDUX with per-run member masks is far from one result per clock -
+// kept for the record, off by default.)
+// Run sums with ONE warp reduction per value instead of a log-depth scan: every run agrees on a power-of-two scale from
+// its largest magnitude (redux.max on the float bit patterns), the values go to 32-bit fixed point (|v| < 2^25, so 32 of
+// them cannot overflow), redux.sync.add over the run's lanes sums them exactly and order-independently, and the result is
+// scaled back.  Quantisation: 2^-25 of the run's largest term per addend - below fp32 summation noise of the same sum.
+// Every lane of the run receives the sums; straight-line code, so runs of one warp do not diverge.
+#ifndef L4D_RUNSUM_REDUX
+#define L4D_RUNSUM_REDUX 0
+#endif
+template <int N>
+__device__ __forceinline__ void l4d_run_sum(float (&v)[N], const WarpRuns& r) {
+  if (r.maxdist == 0) return;                       // warp-uniform: every lane is its own run
+  float am = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) am = fmaxf(am, fabsf(v[i]));
+  const unsigned amb = __reduce_max_sync(r.mask, __float_as_uint(am));      // non-negative floats order like their bits
+  int e = (int)(amb >> 23) - 127;                   // run amax in [2^e, 2^(e+1))
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);        // keep 2^(24-e) and 2^(e-24) normal (|gradients| beyond 2^+-100 do not occur)
+  const float sc = __uint_as_float((unsigned)(127 + 24 - e) << 23), inv = __uint_as_float((unsigned)(127 - 24 + e) << 23);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int q = __reduce_add_sync(r.mask, __float2int_rn(v[i] * sc));
+    v[i] = (float)q * inv;
+  }
+}
 // all 32 lanes must call; g may be zero for lanes without a contribution
 __device__ __forceinline__ void l4d_plane_scatter_warp(float* G, int W, const Bilerp& b, const float g[8]) {
   const WarpRuns r = l4d_warp_runs(b.y0 * W + b.x0);
@@ -215,7 +246,11 @@ __device__ __forceinline__ void l4d_plane_scatter_warp(float* G, int W, const Bi
     float s[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) s[c] = g[c] * wgt[k];
+#if L4D_RUNSUM_REDUX
+    l4d_run_sum<8>(s, r);
+#else
     l4d_seg_sum8(s, r);
+#endif
     if (r.tail) {
       float* p = G + ((size_t)ys[k] * W + xs[k]) * 8;
       l4d_red4(p, s[0], s[1], s[2], s[3]);
@@ -229,8 +264,13 @@ __device__ __forceinline__ void l4d_plane_scatter_warp_t(float* G, int W, const 
   float s0[8], s1[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) { s0[c] = g[c] * b.wx0; s1[c] = g[c] * b.wx1; }
+#if L4D_RUNSUM_REDUX
+  l4d_run_sum<8>(s0, r);
+  l4d_run_sum<8>(s1, r);
+#else
   l4d_seg_sum8(s0, r);
   l4d_seg_sum8(s1, r);
+#endif
   if (r.tail) {
     float* p00 = G + ((size_t)b.y0 * W + b.x0) * 8;
     float* p01 = G + ((size_t)b.y0 * W + b.x1) * 8;
