@@ -197,16 +197,27 @@ __device__ __forceinline__ WarpRuns l4d_warp_runs(int key) {
 }
 // inclusive segmented scans of 8 values at once (8 independent shuffles per step); the tail lane of a run ends up
 // with the run's sums
+#ifndef L4D_SCAN_FMA
+#define L4D_SCAN_FMA 1
+#endif
 __device__ __forceinline__ void l4d_seg_sum8(float (&v)[8], const WarpRuns& r) {
   // only as many steps as the longest run of the warp needs (measured against a fixed 5-step scan: 14.2 -> 11.8 ms)
 #pragma unroll 1
   for (int d = 1; d <= r.maxdist; d <<= 1) {
+#if L4D_SCAN_FMA
+    // one FFMA per value instead of FSEL + FADD (the scans are 40 % of this kernel's instructions): fma(t, 1, v) rounds
+    // like t + v, fma(t, 0, v) = v for every finite t
+    const float take = r.dist >= d ? 1.0f : 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = fmaf(__shfl_up_sync(0xffffffffu, v[c], d), take, v[c]);
+#else
     const bool take = r.dist >= d;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float t = __shfl_up_sync(0xffffffffu, v[c], d);
       v[c] += take ? t : 0.f;
     }
+#endif
   }
 }
 // (A/B option, measured 3.5x SLOWER than the scans - REDUX with per-run member masks is far from one result per clock -
@@ -324,6 +335,76 @@ struct DfeatFromPlane {
 #define L4D_SC_TIME_PLANES 2
 #define L4D_SC_DYNAMIC_HASH 4
 #define L4D_SC_ALL 7
+// Dynamic-hash gradient REDs are issued in slices BETWEEN the plane queries (L4D_SCATTER_INTERLEAVE): the plane sinks are
+// instruction-issue / shuffle work, the 12 L REDs of a sample are pure LSU / L2-atomic work (1.5 SM-cycles per lane-op,
+// profiles/r02_micro_red.txt); issued back to back at the end they fill the RED queue while the ALUs idle
+// (k_bwd_scatter = time-plane kernel + hash kernel, nearly added up: DESIGN 9).  0 = all at the end (round-1 order),
+// 1 = one slice per time-plane query, 2 = one slice per plane sink.
+#ifndef L4D_SCATTER_INTERLEAVE
+#define L4D_SCATTER_INTERLEAVE 2
+#endif
+struct DynHashCursor {
+  int p, l;            // next (plane, level)
+  float dq[4];         // dL/dfeature of levels (l & ~3) .. +3 of plane p (valid when the level count is a multiple of 4)
+};
+// up to n (plane, level) pairs of the dynamic-hash gradient: only the (x,t) query carries gradient
+// (lidar4d.py:160-161,169-170 are no_grad)
+template <class DF>
+L4D_HD void l4d_bw_dynhash_slice(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z, float wc,
+                                 const DF& l4d_dfeat_fn, int row_hash_d, DynHashCursor& cur, int n) {
+  const int L = (int)M.gs.n_levels;
+  const bool quads = (L & 3) == 0;             // rows of a plane start on a multiple of 4: one 16-byte load per 4 levels
+#pragma unroll 1
+  for (; n > 0 && cur.p < 3; --n) {
+    const int p = cur.p, l = cur.l;
+    const float ca = p == 2 ? y : x, cb = p == 0 ? y : z;
+    uint32_t idx[4]; float w[4];
+    l4d_corners2(M.gd[p], l, ca, cb, idx, w);
+    if (quads && (l & 3) == 0) l4d_dfeat_fn.ld4(row_hash_d + p * L + l, cur.dq);
+    const int li = l & 3;
+    const float dsel = li == 0 ? cur.dq[0] : (li == 1 ? cur.dq[1] : (li == 2 ? cur.dq[2] : cur.dq[3]));
+    const float d = wc * (quads ? dsel : l4d_dfeat_fn(row_hash_d + p * L + l));
+    float* gcomb = G.hd_comb[p];
+    if (gcomb) {
+      // comb[entry] accumulates w_corner * d: ONE float per entry (the four features of an entry get basis[k] times it,
+      // and the slice weights, in k_fold_dynamic).  The two x-corners of a cell are neighbours in the table (index =
+      // cx ^ h(cy) or cx + cy * res) and fall into the same aligned quad of entries three times out of four: they go out
+      // as one 16-byte RED on that quad, 2.5 instead of 4 L2 atomic operations per level (the backward is bound by them:
+      // 1.5 SM-cycles per lane-operation whatever its width, profiles/r02_micro_red.txt).
+      float* cb = gcomb + M.gd[p].offset[l];          // level offsets are multiples of 8 entries: quads stay 16-byte aligned
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const uint32_t i0 = idx[2 * r], i1 = idx[2 * r + 1];
+        const float a = w[2 * r] * d, b = w[2 * r + 1] * d;
+        const bool same = (i0 >> 2) == (i1 >> 2);
+        const uint32_t s0 = i0 & 3u, s1 = same ? (i1 & 3u) : 4u;
+        l4d_red4(cb + (i0 & ~3u), (s0 == 0u ? a : 0.f) + (s1 == 0u ? b : 0.f), (s0 == 1u ? a : 0.f) + (s1 == 1u ? b : 0.f),
+                 (s0 == 2u ? a : 0.f) + (s1 == 2u ? b : 0.f), (s0 == 3u ? a : 0.f) + (s1 == 3u ? b : 0.f));
+        if (!same) l4d_red1(cb + i1, b);
+      }
+    } else {
+      const float e0 = d * F.cur.basis[0], e1 = d * F.cur.basis[1], e2 = d * F.cur.basis[2], e3 = d * F.cur.basis[3];
+      const size_t off = (size_t)M.gd[p].offset[l] * 4;
+      float* glo = G.hd[p][F.cur.slice_lo];
+      float* ghi = G.hd[p][F.cur.slice_hi];
+      const float slo = F.cur.single ? 1.0f : F.cur.w_lo;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float ww = w[c] * slo;
+        l4d_red4(glo + off + (size_t)idx[c] * 4, ww * e0, ww * e1, ww * e2, ww * e3);
+      }
+      if (!F.cur.single) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float ww = w[c] * F.cur.w_hi;
+          l4d_red4(ghi + off + (size_t)idx[c] * 4, ww * e0, ww * e1, ww * e2, ww * e3);
+        }
+      }
+    }
+    if (++cur.l == L) { cur.l = 0; ++cur.p; }
+  }
+}
+
 template <bool WARP_AGG, class DF, bool STATIC_HASH = true, int PARTS = L4D_SC_ALL>
 L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
                              const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6], bool active);
@@ -352,6 +433,15 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
   l4d_agg_weights(F, wc, wf, wb);
   const float xf0 = x + flow[0], xf1 = y + flow[1], xf2 = z + flow[2];
   const float xw0 = x + flow[3], xw1 = y + flow[4], xw2 = z + flow[5];
+  // dynamic-hash REDs are spread over the plane work (see L4D_SCATTER_INTERLEAVE above)
+  DynHashCursor hc;
+  hc.p = (PARTS & L4D_SC_DYNAMIC_HASH) ? 0 : 3;
+  hc.l = 0;
+  hc.dq[0] = hc.dq[1] = hc.dq[2] = hc.dq[3] = 0.f;
+  const int hslots = L4D_SCATTER_INTERLEAVE == 2 ? nS * 12 : nS * 3;
+  const int hper = L4D_SCATTER_INTERLEAVE ? (3 * L + hslots - 1) / hslots : 0;
+#define L4D_DYNHASH_SLICE(mode, n) \
+  do { if (L4D_SCATTER_INTERLEAVE == (mode) && active) l4d_bw_dynhash_slice(M, F, G, x, y, z, wc, l4d_dfeat_fn, row_hash_d, hc, (n)); } while (0)
 
 #pragma unroll 1
   for (int sc = 0; sc < nS; ++sc) {
@@ -368,12 +458,15 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
 #pragma unroll
       for (int c = 0; c < 8; ++c) g[c] = d[c] * v1[c] * v2[c];
       l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][0], R, b0, g, false);
+      L4D_DYNHASH_SLICE(2, hper);
 #pragma unroll
       for (int c = 0; c < 8; ++c) g[c] = d[c] * v0[c] * v2[c];
       l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][1], R, b1, g, false);
+      L4D_DYNHASH_SLICE(2, hper);
 #pragma unroll
       for (int c = 0; c < 8; ++c) g[c] = d[c] * v0[c] * v1[c];
       l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][3], R, b2, g, false);
+      L4D_DYNHASH_SLICE(2, hper);
     }
     if (PARTS & L4D_SC_TIME_PLANES) {   // time planes (x,t) (y,t) (z,t): three queries, warped ones also feed d(coords) -> flow
       float d[8];
@@ -396,14 +489,18 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v1[c] * v2[c]; c0 = fmaf(g[c], x0[c], c0); }
         l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][2], R, b0, g, true);
+        L4D_DYNHASH_SLICE(2, hper);
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v0[c] * v2[c]; c1 = fmaf(g[c], x1[c], c1); }
         l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][4], R, b1, g, true);
+        L4D_DYNHASH_SLICE(2, hper);
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v0[c] * v1[c]; c2 = fmaf(g[c], x2[c], c2); }
         l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][5], R, b2, g, true);
+        L4D_DYNHASH_SLICE(2, hper);
         if (qi == 1) { dflow[0] += c0; dflow[1] += c1; dflow[2] += c2; }
         if (qi == 2) { dflow[3] += c0; dflow[4] += c1; dflow[5] += c2; }
+        L4D_DYNHASH_SLICE(1, hper);
       }
     }
   }
@@ -423,45 +520,9 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
     for (int c = 0; c < 8; ++c) l4d_red4(base + (size_t)idx[c] * 4, w[c] * d0, w[c] * d1, w[c] * d2, w[c] * d3);
   }
 
-  // dynamic hash: only the (x,t) query carries gradient (lidar4d.py:160-161,169-170 are no_grad)
-#pragma unroll 1
-  for (int p = 0; (PARTS & L4D_SC_DYNAMIC_HASH) && p < 3; ++p) {
-    const float ca = p == 2 ? y : x, cb = p == 0 ? y : z;
-    float* glo = G.hd[p][F.cur.slice_lo];
-    float* ghi = G.hd[p][F.cur.slice_hi];
-    float* gcomb = G.hd_comb[p];
-    float dq[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool quads = (L & 3) == 0;             // rows of a plane start on a multiple of 4: one 16-byte load per 4 levels
-#pragma unroll 1
-    for (int l = 0; l < L; ++l) {
-      uint32_t idx[4]; float w[4];
-      l4d_corners2(M.gd[p], l, ca, cb, idx, w);
-      if (quads && (l & 3) == 0) l4d_dfeat_fn.ld4(row_hash_d + p * L + l, dq);
-      const int li = l & 3;
-      const float dsel = li == 0 ? dq[0] : (li == 1 ? dq[1] : (li == 2 ? dq[2] : dq[3]));
-      const float d = wc * (quads ? dsel : l4d_dfeat_fn(row_hash_d + p * L + l));
-      const float e0 = d * F.cur.basis[0], e1 = d * F.cur.basis[1], e2 = d * F.cur.basis[2], e3 = d * F.cur.basis[3];
-      const float slo = F.cur.single ? 1.0f : F.cur.w_lo;
-      const size_t off = (size_t)M.gd[p].offset[l] * 4;
-      if (gcomb) {          // slice weights are applied by k_fold_dynamic
-#pragma unroll
-        for (int c = 0; c < 4; ++c) l4d_red4(gcomb + off + (size_t)idx[c] * 4, w[c] * e0, w[c] * e1, w[c] * e2, w[c] * e3);
-        continue;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float ww = w[c] * slo;
-        l4d_red4(glo + off + (size_t)idx[c] * 4, ww * e0, ww * e1, ww * e2, ww * e3);
-      }
-      if (!F.cur.single) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float ww = w[c] * F.cur.w_hi;
-          l4d_red4(ghi + off + (size_t)idx[c] * 4, ww * e0, ww * e1, ww * e2, ww * e3);
-        }
-      }
-    }
-  }
+  // dynamic hash: whatever the slices above did not cover (all of it when L4D_SCATTER_INTERLEAVE == 0)
+  l4d_bw_dynhash_slice(M, F, G, x, y, z, wc, l4d_dfeat_fn, row_hash_d, hc, 3 * L);
+#undef L4D_DYNHASH_SLICE
 }
 
 // ---- B5: flow MLP backprop.  g[6] = dL/dflow of this sample. ----------------------------

@@ -62,6 +62,11 @@ struct DevModel {
   const __half* hd[3];          // dynamic tables [pair k = slices k,k+1][entries][lo 4 | hi 4]
   const __half* hf;             // flow table     [entries][8]
   uint32_t hd_slice_entries[3]; // entries per time slice
+  // optional, per launch (split pipeline): the dynamic tables contracted with the frame's time constants, ONE fp32 per
+  // entry and time query (cur, fwd, bwd): con[e] = sum_k basis[k] * (w_lo * T_lo[e][k] + w_hi * T_hi[e][k]).  Every sample
+  // of a launch shares the frame, and the feature is linear in the table, so k_contract_dynamic does this once per entry
+  // instead of once per corner of every sample, and the gather reads 4 bytes per corner instead of a 16-byte pair record.
+  const float* hd_con[3][3];    // [plane][query][entries]; nullptr = gather from the pair records
   const float* planes[L4D_MAX_PLANE_SCALES][6];   // channels-last [H][W][8]
   uint32_t plane_res[L4D_MAX_PLANE_SCALES];
   uint32_t n_scales, time_res;
@@ -85,7 +90,7 @@ struct DevGrads {
   // optional work accumulators (split pipeline): every sample of a launch shares the frame, hence the time-slice
   // weights and the Lagrange basis, so the scatter kernels reduce the slice- / basis-independent part once per corner
   // and k_fold_* distributes it afterwards: half the reductions.
-  float* hd_comb[3];                           // [entries][4]  sum of w_corner * d * basis[0..4) (before the slice weights)
+  float* hd_comb[3];                           // [entries]  sum of w_corner * d (before the time basis and the slice weights)
   float* hf_comb;                              // [entries][2]  sum of w_corner * dFin[2l + c]   (before the basis)
   float* planes_cl[L4D_MAX_PLANE_SCALES][6];   // channels-last work grads
   float *sig_w1t, *sig_w2;                     // [in_pad][64], [16][64]
@@ -324,6 +329,48 @@ L4D_HD float l4d_encode2_time(const DevGrid& g, const __half* table, uint32_t sl
     for (int i = 0; i < 4; ++i) fl[i] = wl * fl[i] + wh * fh[i];
   }
   return ((q.basis[0] * fl[0] + q.basis[1] * fl[1]) + q.basis[2] * fl[2]) + q.basis[3] * fl[3];
+}
+
+// the time-dependent part of l4d_encode2_time for ONE table entry: rec = pair record {lo f0..f3, hi f0..f3} (fp16) of the
+// query's pair; same arithmetic as there with the corner blend factored out (the blend is linear)
+L4D_HD uint32_t l4d_time_pair(const L4DTimeQuery& q, uint32_t n_slices) { return q.slice_lo < n_slices - 1u ? q.slice_lo : n_slices - 2u; }
+L4D_HD float l4d_contract_entry(uint4 rec, const L4DTimeQuery& q, uint32_t n_slices) {
+  const uint32_t pair = l4d_time_pair(q, n_slices);
+  const float wl = q.single ? (q.slice_lo == pair ? 1.0f : 0.0f) : q.w_lo;
+  const float wh = q.single ? 1.0f - wl : q.w_hi;
+  const float2 a = l4d_h2f(rec.x), b = l4d_h2f(rec.y), cc = l4d_h2f(rec.z), d = l4d_h2f(rec.w);
+  float fl[4] = {a.x, a.y, b.x, b.y};
+  const float fh[4] = {cc.x, cc.y, d.x, d.y};
+  if (q.single) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fl[i] = wl != 0.f ? fl[i] : fh[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fl[i] = wl * fl[i] + wh * fh[i];
+  }
+  return ((q.basis[0] * fl[0] + q.basis[1] * fl[1]) + q.basis[2] * fl[2]) + q.basis[3] * fl[3];
+}
+// one level of one contracted dynamic table at (x,y): bilinear blend of four fp32 entries.  The two x-corners of a cell
+// are neighbours in the table (index = cx ^ h(cy) or cx + cy * res) and share an aligned quad of entries three times out
+// of four: one 16-byte load serves both (2.5 instead of 4 divergent requests per level; the forward is bound by the
+// L1TEX pipe that serves them).
+L4D_HD float l4d_encode2_con(const DevGrid& g, const float* con, int l, float x, float y) {
+  uint32_t idx[4]; float w[4];
+  l4d_corners2(g, l, x, y, idx, w);
+  const float* base = con + g.offset[l];          // level offsets are multiples of 8 entries: quads are 16-byte aligned
+  float out = 0.f;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const uint32_t i0 = idx[2 * r], i1 = idx[2 * r + 1];
+    const float4 q = l4d_ld4(base + (i0 & ~3u));
+    const uint32_t s0 = i0 & 3u, s1 = i1 & 3u;
+    const float v0 = s0 == 0u ? q.x : (s0 == 1u ? q.y : (s0 == 2u ? q.z : q.w));
+    float v1 = s1 == 0u ? q.x : (s1 == 1u ? q.y : (s1 == 2u ? q.z : q.w));
+    if ((i0 >> 2) != (i1 >> 2)) v1 = l4d_ld1(base + i1);
+    out = fmaf(w[2 * r], v0, out);
+    out = fmaf(w[2 * r + 1], v1, out);
+  }
+  return out;
 }
 
 // ---------------------------------------------------------------------------
@@ -718,12 +765,23 @@ L4D_HD void l4d_gather_features(const DevModel& M, const L4DFrame& F, float x, f
     const float ca = p == 2 ? y : x, cb = p == 0 ? y : z;           // (x,y) (x,z) (y,z)
     const float fa = p == 2 ? xf1 : xf0, fb = p == 0 ? xf1 : xf2;
     const float ba = p == 2 ? xw1 : xw0, bb = p == 0 ? xw1 : xw2;
+    const float* const* con = M.hd_con[p];
+    if (con[0]) {        // contracted tables of this launch (k_contract_dynamic)
 #pragma unroll 1
-    for (int l = 0; l < L; ++l) {
-      float v = wc * l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], M.time_res, F.cur, l, ca, cb);
-      if (wf != 0.f) v = fmaf(wf, l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], M.time_res, F.fwd, l, fa, fb), v);
-      if (wb != 0.f) v = fmaf(wb, l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], M.time_res, F.bwd, l, ba, bb), v);
-      xb[l * xs] = v;
+      for (int l = 0; l < L; ++l) {
+        float v = wc * l4d_encode2_con(M.gd[p], con[0], l, ca, cb);
+        if (wf != 0.f) v = fmaf(wf, l4d_encode2_con(M.gd[p], con[1], l, fa, fb), v);
+        if (wb != 0.f) v = fmaf(wb, l4d_encode2_con(M.gd[p], con[2], l, ba, bb), v);
+        xb[l * xs] = v;
+      }
+    } else {
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        float v = wc * l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], M.time_res, F.cur, l, ca, cb);
+        if (wf != 0.f) v = fmaf(wf, l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], M.time_res, F.fwd, l, fa, fb), v);
+        if (wb != 0.f) v = fmaf(wb, l4d_encode2_time(M.gd[p], M.hd[p], M.hd_slice_entries[p], M.time_res, F.bwd, l, ba, bb), v);
+        xb[l * xs] = v;
+      }
     }
     l4d_emit<ACC>(acc, M, xb, xs, row_hash_d + p * L, L, sink);
   }

@@ -96,7 +96,7 @@ static inline GradWorkLayout grad_work_layout(const L4DConfig* c) {
   L.flo_w0t = take(16 * 64 * f);
   L.flo_w1t = take(64 * 64 * f);
   L.flo_w2 = take(8 * 64 * f);
-  for (int p = 0; p < 3; ++p) L.hd_comb[p] = take((size_t)c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels] * 4 * f);
+  for (int p = 0; p < 3; ++p) L.hd_comb[p] = take((size_t)c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels] * f);
   L.hf_comb = take((size_t)c->flow.offset[c->flow.n_levels] * 2 * f);
   L.total = o;
   return L;
@@ -108,6 +108,10 @@ static inline int check_config(const L4DConfig* c) {
   for (int p = 0; p < 3; ++p) {
     if (c->hash_dynamic[p].n_dims != 2 || c->hash_dynamic[p].n_features != 4) return l4d_fail(L4D_EINVAL, "hash_dynamic must be 2D F=4");
     if (c->hash_dynamic[p].n_levels != c->hash_static.n_levels) return l4d_fail(L4D_EINVAL, "hash level counts differ");
+    // tiny-cuda-nn rounds every level up to a multiple of 8 entries; the scalar per-entry accumulators / contracted tables
+    // of the dynamic hash are accessed as aligned quads of entries and rely on it
+    for (uint32_t l = 0; l <= c->hash_dynamic[p].n_levels && l <= L4D_MAX_LEVELS; ++l)
+      if (c->hash_dynamic[p].offset[l] % 8u) return l4d_fail(L4D_EINVAL, "hash_dynamic level offsets must be multiples of 8 entries");
   }
   if (c->flow.n_dims != 3 || c->flow.n_features != 8 || c->flow.n_levels != 8) return l4d_fail(L4D_EINVAL, "flow grid must be 3D F=8 L=8");
   if (c->hash_static.n_levels < 1 || c->hash_static.n_levels > L4D_MAX_LEVELS) return l4d_fail(L4D_EINVAL, "bad n_levels");
@@ -196,7 +200,7 @@ static inline void build_grads(const L4DConfig* c, const L4DMasterGrads* g, void
 
 #define L4D_NT 128
 #define L4D_BWD_SCRATCH_CTAS 1024
-struct SavedLayout { size_t feat, flow_in, sigma, attr, hidden, flow, dfeat, dflow, tstart, total; };
+struct SavedLayout { size_t feat, flow_in, sigma, attr, hidden, flow, dfeat, dflow, tstart, hd_con, total; };
 static inline SavedLayout saved_layout(const L4DConfig* c, uint32_t n_rays, uint32_t S) {
   SavedLayout L;
   const size_t P = (size_t)n_rays * S;
@@ -215,8 +219,22 @@ static inline SavedLayout saved_layout(const L4DConfig* c, uint32_t n_rays, uint
   L.dfeat = take(tiles * ((c->sigma_in_dim + 3) / 4) * 2048);
   L.dflow = take(P * 6 * sizeof(float));
   L.tstart = take(tiles * sizeof(float));
+  // contracted dynamic tables of the launch (DevModel::hd_con): [query cur|fwd|bwd][plane][entries] fp32
+  size_t dyn_entries = 0;
+  for (int p = 0; p < 3; ++p) dyn_entries += c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels];
+  L.hd_con = take(3 * dyn_entries * sizeof(float));
   L.total = o;
   return L;
+}
+// DevModel::hd_con inside the saved buffer of a launch (level offsets, hence plane sizes, are multiples of 8 entries)
+static inline void point_contracted(const L4DConfig* c, void* saved, uint32_t n_rays, uint32_t S, DevModel& M) {
+  SavedLayout L = saved_layout(c, n_rays, S);
+  float* b = reinterpret_cast<float*>(reinterpret_cast<char*>(saved) + L.hd_con);
+  for (int q = 0; q < 3; ++q)
+    for (int p = 0; p < 3; ++p) {
+      M.hd_con[p][q] = b;
+      b += c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels];
+    }
 }
 static inline SavedView saved_view(const L4DConfig* c, void* saved, uint32_t n_rays, uint32_t S) {
   SavedLayout L = saved_layout(c, n_rays, S);

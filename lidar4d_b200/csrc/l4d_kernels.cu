@@ -139,22 +139,46 @@ __global__ void k_add(const float* __restrict__ src, float* __restrict__ dst, in
   if (i < n) dst[i] += src[i];
 }
 
-// distribute the slice-independent dynamic-hash gradient over the two live time slices and clear it (DevGrads::hd_comb)
-__global__ void k_fold_dynamic(float4* __restrict__ comb, float4* __restrict__ glo, float4* __restrict__ ghi, size_t n,
-                               float w_lo, float w_hi) {
+// distribute the slice-independent dynamic-hash gradient (DevGrads::hd_comb: one float per entry = sum of w_corner * d)
+// over the four time-basis features of the entry and the two live time slices, and clear it
+__global__ void k_fold_dynamic(float* __restrict__ comb, float4* __restrict__ glo, float4* __restrict__ ghi, size_t n,
+                               float w_lo, float w_hi, float b0, float b1, float b2, float b3) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float4 c = comb[i];
-  if (c.x == 0.f && c.y == 0.f && c.z == 0.f && c.w == 0.f) return;
+  const float c = comb[i];
+  if (c == 0.f) return;
+  const float e0 = c * b0, e1 = c * b1, e2 = c * b2, e3 = c * b3;
   float4 a = glo[i];
-  a.x = fmaf(w_lo, c.x, a.x); a.y = fmaf(w_lo, c.y, a.y); a.z = fmaf(w_lo, c.z, a.z); a.w = fmaf(w_lo, c.w, a.w);
+  a.x = fmaf(w_lo, e0, a.x); a.y = fmaf(w_lo, e1, a.y); a.z = fmaf(w_lo, e2, a.z); a.w = fmaf(w_lo, e3, a.w);
   glo[i] = a;
   if (ghi) {
     float4 b = ghi[i];
-    b.x = fmaf(w_hi, c.x, b.x); b.y = fmaf(w_hi, c.y, b.y); b.z = fmaf(w_hi, c.z, b.z); b.w = fmaf(w_hi, c.w, b.w);
+    b.x = fmaf(w_hi, e0, b.x); b.y = fmaf(w_hi, e1, b.y); b.z = fmaf(w_hi, e2, b.z); b.w = fmaf(w_hi, e3, b.w);
     ghi[i] = b;
   }
-  comb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  comb[i] = 0.f;
+}
+// DevModel::hd_con: contract the pair records of one dynamic table with the time constants of the frame's queries
+// (l4d_contract_entry), one thread per entry.  25 MB read + 9 MB written at L = 16: microseconds, once per launch.
+struct ContractArgs {
+  const uint4* table[3];      // [pair][entries] records of plane p
+  float* con[3][3];           // [plane][query]
+  uint32_t entries[3];
+  uint32_t n_slices, n_queries_mask;      // bit q set: query q (cur, fwd, bwd) is live
+  L4DTimeQuery q[3];
+};
+__global__ void k_contract_dynamic(const __grid_constant__ ContractArgs A) {
+  const uint32_t p = blockIdx.y;
+  const uint32_t n = A.entries[p];
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int qi = 0; qi < 3; ++qi) {
+      if (!((A.n_queries_mask >> qi) & 1u)) continue;
+      const uint32_t pair = l4d_time_pair(A.q[qi], A.n_slices);
+      const uint4 rec = __ldg(A.table[p] + (size_t)pair * n + e);
+      A.con[p][qi][e] = l4d_contract_entry(rec, A.q[qi], A.n_slices);
+    }
+  }
 }
 // flow grid: feature (2i + c) of an entry gets basis[i] * comb[entry][c] (DevGrads::hf_comb), then clear
 __global__ void k_fold_flow(float2* __restrict__ comb, float4* __restrict__ g, size_t n, float b0, float b1, float b2, float b3) {
@@ -1099,6 +1123,26 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
   A.depth = depth; A.image = image; A.wsum = wsum; A.weights = weights; A.zvals = zvals;
   A.train = 1u;
   const size_t P = (size_t)rays->n_rays * rays->n_steps;
+  {
+    static const char* e = getenv("L4D_NO_CONTRACT");        // A/B knob: gather from the pair records as in round 1
+    if (!(e && atoi(e) != 0)) {
+      point_contracted(cfg, saved, rays->n_rays, rays->n_steps, A.M);
+      ContractArgs C;
+      memset(&C, 0, sizeof(C));
+      uint32_t nmax = 0;
+      for (int p = 0; p < 3; ++p) {
+        C.table[p] = reinterpret_cast<const uint4*>(A.M.hd[p]);
+        C.entries[p] = A.M.hd_slice_entries[p];
+        nmax = C.entries[p] > nmax ? C.entries[p] : nmax;
+        for (int q = 0; q < 3; ++q) C.con[p][q] = const_cast<float*>(A.M.hd_con[p][q]);
+      }
+      C.n_slices = cfg->time_resolution;
+      C.n_queries_mask = 1u | (frame->has_fwd ? 2u : 0u) | (frame->has_bwd ? 4u : 0u);
+      C.q[0] = frame->cur; C.q[1] = frame->fwd; C.q[2] = frame->bwd;
+      ++g_launches; k_contract_dynamic<<<dim3((unsigned)nblk(nmax), 3), 256, 0, st>>>(C);
+      prof_mark(st, "k_contract_dynamic");
+    }
+  }
   if (cfg->mlp_fp16) {
     {
       const size_t smem = flow_tc_smem().total_fwd + 1024;
@@ -1232,10 +1276,11 @@ extern "C" int l4d_render_backward_ex(const L4DConfig* cfg, const void* staged, 
       for (int p = 0; p < 3; ++p) {
         const size_t n = cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels];
         const bool single = frame->cur.single != 0;
-        ++g_launches; k_fold_dynamic<<<nblk(n), 256, 0, st>>>(reinterpret_cast<float4*>(A.G.hd_comb[p]),
+        const float* tb = frame->cur.basis;
+        ++g_launches; k_fold_dynamic<<<nblk(n), 256, 0, st>>>(A.G.hd_comb[p],
                                                reinterpret_cast<float4*>(A.G.hd[p][frame->cur.slice_lo]),
                                                single ? nullptr : reinterpret_cast<float4*>(A.G.hd[p][frame->cur.slice_hi]), n,
-                                               single ? 1.0f : frame->cur.w_lo, frame->cur.w_hi);
+                                               single ? 1.0f : frame->cur.w_lo, frame->cur.w_hi, tb[0], tb[1], tb[2], tb[3]);
       }
       prof_mark(st, "k_fold_dynamic");
       // hash_static and hash_dynamic gradients are final from here on (the flow backward below only touches the flow net)

@@ -133,6 +133,27 @@ extern "C" int hs_render_forward(const L4DConfig* cfg, const void* staged, const
   SavedView sv;
   memset(&sv, 0, sizeof(sv));
   if (saved) sv = saved_view(cfg, saved, rays->n_rays, S);
+  // rays->reserved bit 2 (host-sim only): gather the dynamic hash from the per-launch contracted tables, built here the way
+  // k_contract_dynamic builds them (DevModel::hd_con)
+  std::vector<float> con_store;
+  if (rays->reserved & 4u) {
+    size_t tot = 0;
+    for (int p = 0; p < 3; ++p) tot += M.hd_slice_entries[p];
+    con_store.assign(3 * tot, 0.f);
+    float* b = con_store.data();
+    const L4DTimeQuery* qs[3] = {&frame->cur, &frame->fwd, &frame->bwd};
+    const bool live[3] = {true, frame->has_fwd != 0, frame->has_bwd != 0};
+    for (int q = 0; q < 3; ++q)
+      for (int p = 0; p < 3; ++p) {
+        const uint32_t n = M.hd_slice_entries[p];
+        M.hd_con[p][q] = b;
+        if (live[q]) {
+          const uint4* tab = reinterpret_cast<const uint4*>(M.hd[p]) + (size_t)l4d_time_pair(*qs[q], cfg->time_resolution) * n;
+          for (uint32_t e = 0; e < n; ++e) b[e] = l4d_contract_entry(tab[e], *qs[q], cfg->time_resolution);
+        }
+        b += n;
+      }
+  }
   const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, S, rays->perturb, rays->seed);
   for (uint32_t ray = 0; ray < rays->n_rays; ++ray) {
     const float* o = rays->rays_o + 3 * ray;
@@ -296,14 +317,17 @@ extern "C" int hs_render_backward(const L4DConfig* cfg, const void* staged, cons
     const bool single = F.cur.single != 0;
     const float w_lo = single ? 1.0f : F.cur.w_lo, w_hi = F.cur.w_hi;
     for (int p = 0; p < 3; ++p) {
-      const size_t n = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels] * 4;
+      const size_t n = (size_t)cfg->hash_dynamic[p].offset[cfg->hash_dynamic[p].n_levels];
       float* c = G.hd_comb[p];
       float* glo = G.hd[p][F.cur.slice_lo];
       float* ghi = single ? nullptr : G.hd[p][F.cur.slice_hi];
       for (size_t i = 0; i < n; ++i) {
         if (c[i] == 0.f) continue;
-        glo[i] = fmaf(w_lo, c[i], glo[i]);
-        if (ghi) ghi[i] = fmaf(w_hi, c[i], ghi[i]);
+        for (int k = 0; k < 4; ++k) {
+          const float e = c[i] * F.cur.basis[k];
+          glo[4 * i + k] = fmaf(w_lo, e, glo[4 * i + k]);
+          if (ghi) ghi[4 * i + k] = fmaf(w_hi, e, ghi[4 * i + k]);
+        }
         c[i] = 0.f;
       }
     }

@@ -64,9 +64,11 @@ class HostSim:
         r.seed, r.ray_offset = seed, ray_offset
         return r
 
-    def render(self, ro, rd, time, S, perturb=False, seed=0, ray_offset=0, train=False):
+    def render(self, ro, rd, time, S, perturb=False, seed=0, ray_offset=0, train=False, contracted=False):
+        """contracted=True: dynamic hash gathered from the per-launch contracted tables (k_contract_dynamic's mirror)"""
         fr = self.frame(time)
         rays = self._rays(ro, rd, S, perturb, seed, ray_offset)
+        rays.reserved = 4 if contracted else 0
         N = rays.n_rays
         out = {k: torch.zeros(s) for k, s in [("depth", N), ("image", (N, 2)), ("wsum", N),
                                                ("weights", (N, S)), ("z_vals", (N, S))]}

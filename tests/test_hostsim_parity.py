@@ -70,6 +70,7 @@ def test_render_forward_backward(t, S, perturb, seed, surface):
     N = ro.shape[0]
     ref = orc.render(torch.from_numpy(ro), torch.from_numpy(rd), t, num_steps=S, perturb=perturb, seed=seed,
                      return_stages=True)
+    gc = hs.render(ro, rd, t, S, perturb=perturb, seed=seed, contracted=True)
     got = hs.render(ro, rd, t, S, perturb=perturb, seed=seed, train=True)
     frac = float(ref["mask"].float().mean())
     if surface:
@@ -78,6 +79,10 @@ def test_render_forward_backward(t, S, perturb, seed, surface):
     assert np.array_equal(got["z_vals"].numpy(), ref["z_vals"].numpy())          # sampling is bit-exact
     for k, ko in [("depth", "depth_lidar"), ("image", "image_lidar"), ("wsum", "weights_sum_lidar"), ("weights", "weights")]:
         assert rel_err(got[k], ref[ko]) < TOL, k
+    # same through the per-launch contracted dynamic tables + quad loads of the split pipeline's gather
+    for k, ko in [("depth", "depth_lidar"), ("image", "image_lidar"), ("wsum", "weights_sum_lidar"), ("weights", "weights")]:
+        assert rel_err(gc[k], ref[ko]) < TOL, k
+        assert rel_err(gc[k], got[k]) < (TOL if k == "weights" else 1e-5), k      # per-sample weights: 3e-5 either way
     g = torch.Generator().manual_seed(1)
     gd, gi = torch.randn(N, generator=g), torch.randn(N, 2, generator=g)
     gw, gww = torch.randn(N, generator=g) * 0.1, torch.randn(N, S, generator=g) * 0.01
