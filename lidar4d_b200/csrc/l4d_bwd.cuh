@@ -299,8 +299,39 @@ __device__ __forceinline__ void l4d_plane_scatter_warp_t(float* G, int W, const 
     }
   }
 }
+// gradient rows of the contracted time planes (DevGrads::pl_rows): the same run sums, and the tail lane only issues the two
+// texels of the row - the time-row weights are applied once per launch by k_fold_planes
+__device__ __forceinline__ void l4d_row_scatter_warp(float* Grow, const Bilerp& b, const float g[8]) {
+  const WarpRuns r = l4d_warp_runs(b.x0);
+  float s0[8], s1[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { s0[c] = g[c] * b.wx0; s1[c] = g[c] * b.wx1; }
+#if L4D_RUNSUM_REDUX
+  l4d_run_sum<8>(s0, r);
+  l4d_run_sum<8>(s1, r);
+#else
+  l4d_seg_sum8(s0, r);
+  l4d_seg_sum8(s1, r);
+#endif
+  if (r.tail) {
+    float* p0 = Grow + (size_t)b.x0 * 8;
+    float* p1 = Grow + (size_t)b.x1 * 8;
+    l4d_red4(p0, s0[0], s0[1], s0[2], s0[3]);
+    l4d_red4(p0 + 4, s0[4], s0[5], s0[6], s0[7]);
+    l4d_red4(p1, s1[0], s1[1], s1[2], s1[3]);
+    l4d_red4(p1 + 4, s1[4], s1[5], s1[6], s1[7]);
+  }
+}
 #endif
 
+// sink of a contracted time-plane row
+template <bool WARP_AGG>
+L4D_HD void l4d_row_sink(float* Grow, const Bilerp& b, const float g[8]) {
+#if defined(__CUDA_ARCH__)
+  if (WARP_AGG) { l4d_row_scatter_warp(Grow, b, g); return; }
+#endif
+  l4d_row_scatter(Grow, b, g);
+}
 // plane-gradient sink: plain per-lane REDs, or the warp-aggregated version (device, full warps only)
 template <bool WARP_AGG>
 L4D_HD void l4d_plane_sink(float* G, int W, const Bilerp& b, const float g[8], bool time_plane) {
@@ -335,13 +366,12 @@ struct DfeatFromPlane {
 #define L4D_SC_TIME_PLANES 2
 #define L4D_SC_DYNAMIC_HASH 4
 #define L4D_SC_ALL 7
-// Dynamic-hash gradient REDs are issued in slices BETWEEN the plane queries (L4D_SCATTER_INTERLEAVE): the plane sinks are
-// instruction-issue / shuffle work, the 12 L REDs of a sample are pure LSU / L2-atomic work (1.5 SM-cycles per lane-op,
-// profiles/r02_micro_red.txt); issued back to back at the end they fill the RED queue while the ALUs idle
-// (k_bwd_scatter = time-plane kernel + hash kernel, nearly added up: DESIGN 9).  0 = all at the end (round-1 order),
-// 1 = one slice per time-plane query, 2 = one slice per plane sink.
+// L4D_SCATTER_INTERLEAVE (A/B knob, default off): issue the dynamic-hash REDs in slices BETWEEN the plane sinks instead of back to
+// back at the end (1 = one slice per time-plane query, 2 = one per plane sink).  The idea - the sinks are issue / shuffle work,
+// the REDs L2-atomic work, let them overlap inside a warp - measured SLOWER on the B200: k_bwd_scatter 19.4 ms (0) vs 23.3 ms (2)
+// per 16,384 rays at L = 16 (profiles/r02_v8_ab_contract.txt); the warps of an SM already sit in different phases.
 #ifndef L4D_SCATTER_INTERLEAVE
-#define L4D_SCATTER_INTERLEAVE 2
+#define L4D_SCATTER_INTERLEAVE 0
 #endif
 struct DynHashCursor {
   int p, l;            // next (plane, level)
@@ -405,21 +435,23 @@ L4D_HD void l4d_bw_dynhash_slice(const DevModel& M, const L4DFrame& F, const Dev
   }
 }
 
-template <bool WARP_AGG, class DF, bool STATIC_HASH = true, int PARTS = L4D_SC_ALL>
+template <bool WARP_AGG, class DF, bool STATIC_HASH = true, int PARTS = L4D_SC_ALL, bool ROWS = false>
 L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
                              const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6], bool active);
 
+template <bool ROWS = false>
 L4D_HD void l4d_bw_scatter(const DevModel& M, const L4DFrame& F, const DevGrads& G, BwSample& s) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) s.dflow[k] = 0.f;
   if (!s.active) return;
   DfeatFromDh df{&M, &s};
-  l4d_bw_scatter_t<false>(M, F, G, s.x, s.y, s.z, s.flow, df, s.dflow, true);
+  l4d_bw_scatter_t<false, DfeatFromDh, true, L4D_SC_ALL, ROWS>(M, F, G, s.x, s.y, s.z, s.flow, df, s.dflow, true);
 }
 
+// ROWS: time planes are sampled from DevModel::pl_con and their gradients go to DevGrads::pl_rows (both must be set)
 // WARP_AGG: every lane of the warp must call (lanes without a sample pass active=false and a
 // provider that returns 0; they take part in the plane aggregation with zero contributions)
-template <bool WARP_AGG, class DF, bool STATIC_HASH, int PARTS>
+template <bool WARP_AGG, class DF, bool STATIC_HASH, int PARTS, bool ROWS>
 L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrads& G, float x, float y, float z,
                              const float* flow, const DF& l4d_dfeat_fn, float (&dflow)[6], bool active) {
 #pragma unroll
@@ -482,21 +514,29 @@ L4D_HD void l4d_bw_scatter_t(const DevModel& M, const L4DFrame& F, const DevGrad
         const float tau = qi == 0 ? F.cur.tau : (qi == 1 ? F.fwd.tau : F.bwd.tau);
         float v0[8], v1[8], v2[8], x0[8], x1[8], x2[8], g[8];
         Bilerp b0 = l4d_bilerp(q0, R, tau, T), b1 = l4d_bilerp(q1, R, tau, T), b2 = l4d_bilerp(q2, R, tau, T);
-        l4d_plane_sample<true>(M.planes[sc][2], R, b0, v0, x0);
-        l4d_plane_sample<true>(M.planes[sc][4], R, b1, v1, x1);
-        l4d_plane_sample<true>(M.planes[sc][5], R, b2, v2, x2);
+        // rows: the forward's contracted time planes (2 texels per sample) and their gradient rows, when the launch has them
+        constexpr bool rows = ROWS;       // (a template parameter: the kernel is large, keep the other path out of it)
+        if (rows) {
+          l4d_row_sample<true>(M.pl_con[sc][0][qi], b0, v0, x0);
+          l4d_row_sample<true>(M.pl_con[sc][1][qi], b1, v1, x1);
+          l4d_row_sample<true>(M.pl_con[sc][2][qi], b2, v2, x2);
+        } else {
+          l4d_plane_sample<true>(M.planes[sc][2], R, b0, v0, x0);
+          l4d_plane_sample<true>(M.planes[sc][4], R, b1, v1, x1);
+          l4d_plane_sample<true>(M.planes[sc][5], R, b2, v2, x2);
+        }
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v1[c] * v2[c]; c0 = fmaf(g[c], x0[c], c0); }
-        l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][2], R, b0, g, true);
+        if (rows) l4d_row_sink<WARP_AGG>(G.pl_rows[sc][0][qi], b0, g); else l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][2], R, b0, g, true);
         L4D_DYNHASH_SLICE(2, hper);
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v0[c] * v2[c]; c1 = fmaf(g[c], x1[c], c1); }
-        l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][4], R, b1, g, true);
+        if (rows) l4d_row_sink<WARP_AGG>(G.pl_rows[sc][1][qi], b1, g); else l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][4], R, b1, g, true);
         L4D_DYNHASH_SLICE(2, hper);
 #pragma unroll
         for (int c = 0; c < 8; ++c) { g[c] = wq * d[c] * v0[c] * v1[c]; c2 = fmaf(g[c], x2[c], c2); }
-        l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][5], R, b2, g, true);
+        if (rows) l4d_row_sink<WARP_AGG>(G.pl_rows[sc][2][qi], b2, g); else l4d_plane_sink<WARP_AGG>(G.planes_cl[sc][5], R, b2, g, true);
         L4D_DYNHASH_SLICE(2, hper);
         if (qi == 1) { dflow[0] += c0; dflow[1] += c1; dflow[2] += c2; }
         if (qi == 2) { dflow[3] += c0; dflow[4] += c1; dflow[5] += c2; }

@@ -67,6 +67,10 @@ struct DevModel {
   // of a launch shares the frame, and the feature is linear in the table, so k_contract_dynamic does this once per entry
   // instead of once per corner of every sample, and the gather reads 4 bytes per corner instead of a 16-byte pair record.
   const float* hd_con[3][3];    // [plane][query][entries]; nullptr = gather from the pair records
+  // same idea for the three time planes (x,t) (y,t) (z,t) of every scale: the time coordinate of a query is a launch
+  // constant, so its two plane rows are blended once (k_contract_planes) into ONE row [R][8] per (scale, plane, query) and a
+  // sample reads 2 texels instead of 4.  Indexed [scale][0..2 = planes 2,4,5][query cur|fwd|bwd].
+  const float* pl_con[L4D_MAX_PLANE_SCALES][3][3];
   const float* planes[L4D_MAX_PLANE_SCALES][6];   // channels-last [H][W][8]
   uint32_t plane_res[L4D_MAX_PLANE_SCALES];
   uint32_t n_scales, time_res;
@@ -92,6 +96,9 @@ struct DevGrads {
   // and k_fold_* distributes it afterwards: half the reductions.
   float* hd_comb[3];                           // [entries]  sum of w_corner * d (before the time basis and the slice weights)
   float* hf_comb;                              // [entries][2]  sum of w_corner * dFin[2l + c]   (before the basis)
+  // time-plane gradient rows [R][8] per (scale, plane 2|4|5, query): sum of w_x * g before the two time-row weights of the
+  // query, which k_fold_planes applies (half the reductions of the time-plane sinks)
+  float* pl_rows[L4D_MAX_PLANE_SCALES][3][3];
   float* planes_cl[L4D_MAX_PLANE_SCALES][6];   // channels-last work grads
   float *sig_w1t, *sig_w2;                     // [in_pad][64], [16][64]
   float *att_w1t[2], *att_w2t[2], *att_w3[2];  // [96][64], [64][64], [64]
@@ -350,14 +357,24 @@ L4D_HD float l4d_contract_entry(uint4 rec, const L4DTimeQuery& q, uint32_t n_sli
   }
   return ((q.basis[0] * fl[0] + q.basis[1] * fl[1]) + q.basis[2] * fl[2]) + q.basis[3] * fl[3];
 }
-// one level of one contracted dynamic table at (x,y): bilinear blend of four fp32 entries.  The two x-corners of a cell
-// are neighbours in the table (index = cx ^ h(cy) or cx + cy * res) and share an aligned quad of entries three times out
-// of four: one 16-byte load serves both (2.5 instead of 4 divergent requests per level; the forward is bound by the
-// L1TEX pipe that serves them).
+// one level of one contracted dynamic table at (x,y): bilinear blend of four fp32 entries.
+// L4D_CON_GATHER (A/B, measured on the B200, ms of k_fwd_gather per 16,384 rays at L = 16; pair records: 21.3):
+//   0  one 16-byte load of the aligned quad of entries that holds the first x-corner (the second x-corner is in the same
+//      quad three times out of four) + a conditional 4-byte load otherwise: 2.5 instead of 4 sector requests per level, but
+//      a divergent branch per row - 25.8 ms: the loads of a level no longer overlap
+//   1  four independent 4-byte loads (no branch, no selects)
+//   2  the quad load + an unconditional 4-byte load of the second x-corner
+#ifndef L4D_CON_GATHER
+#define L4D_CON_GATHER 1
+#endif
 L4D_HD float l4d_encode2_con(const DevGrid& g, const float* con, int l, float x, float y) {
   uint32_t idx[4]; float w[4];
   l4d_corners2(g, l, x, y, idx, w);
   const float* base = con + g.offset[l];          // level offsets are multiples of 8 entries: quads are 16-byte aligned
+#if L4D_CON_GATHER == 1
+  const float v0 = l4d_ld1(base + idx[0]), v1 = l4d_ld1(base + idx[1]), v2 = l4d_ld1(base + idx[2]), v3 = l4d_ld1(base + idx[3]);
+  return fmaf(w[3], v3, fmaf(w[2], v2, fmaf(w[1], v1, w[0] * v0)));
+#else
   float out = 0.f;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -365,12 +382,17 @@ L4D_HD float l4d_encode2_con(const DevGrid& g, const float* con, int l, float x,
     const float4 q = l4d_ld4(base + (i0 & ~3u));
     const uint32_t s0 = i0 & 3u, s1 = i1 & 3u;
     const float v0 = s0 == 0u ? q.x : (s0 == 1u ? q.y : (s0 == 2u ? q.z : q.w));
+#if L4D_CON_GATHER == 2
+    const float v1 = l4d_ld1(base + i1);
+#else
     float v1 = s1 == 0u ? q.x : (s1 == 1u ? q.y : (s1 == 2u ? q.z : q.w));
     if ((i0 >> 2) != (i1 >> 2)) v1 = l4d_ld1(base + i1);
+#endif
     out = fmaf(w[2 * r], v0, out);
     out = fmaf(w[2 * r + 1], v1, out);
   }
   return out;
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -426,6 +448,37 @@ L4D_HD void l4d_plane_sample(const float* P, int W, const Bilerp& b, float out[8
   for (int c = 0; c < 8; ++c) {
     out[c] = ((a00[c] * nw + a01[c] * ne) + a10[c] * sw) + a11[c] * se;
     if (WITH_DX) dx[c] = b.gx_mult * ((a01[c] - a00[c]) * b.wy0 + (a11[c] - a10[c]) * b.wy1);
+  }
+}
+
+// one texel of a contracted time-plane row (DevModel::pl_con): the y (time) half of the bilinear blend of
+// l4d_plane_sample, b = l4d_bilerp(any x, W, tau, T)
+L4D_HD float l4d_contract_texel(const float* P, int W, const Bilerp& b, int x, int c) {
+  return P[((size_t)b.y0 * W + x) * 8 + c] * b.wy0 + P[((size_t)b.y1 * W + x) * 8 + c] * b.wy1;
+}
+// 8-channel sample of a contracted row: the x half of the blend; optionally d(out)/d(cx)
+template <bool WITH_DX>
+L4D_HD void l4d_row_sample(const float* row, const Bilerp& b, float out[8], float dx[8]) {
+  const float* p0 = row + (size_t)b.x0 * 8;
+  const float* p1 = row + (size_t)b.x1 * 8;
+  const float4 t0a = l4d_ld4(p0), t0b = l4d_ld4(p0 + 4), t1a = l4d_ld4(p1), t1b = l4d_ld4(p1 + 4);
+  const float a0[8] = {t0a.x, t0a.y, t0a.z, t0a.w, t0b.x, t0b.y, t0b.z, t0b.w};
+  const float a1[8] = {t1a.x, t1a.y, t1a.z, t1a.w, t1b.x, t1b.y, t1b.z, t1b.w};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    out[c] = a0[c] * b.wx0 + a1[c] * b.wx1;
+    if (WITH_DX) dx[c] = b.gx_mult * (a1[c] - a0[c]);
+  }
+}
+// scatter g[8] * the x weights into a gradient row (DevGrads::pl_rows)
+L4D_HD void l4d_row_scatter(float* Grow, const Bilerp& b, const float g[8]) {
+  float* p0 = Grow + (size_t)b.x0 * 8;
+  float* p1 = Grow + (size_t)b.x1 * 8;
+  l4d_red4(p0, g[0] * b.wx0, g[1] * b.wx0, g[2] * b.wx0, g[3] * b.wx0);
+  l4d_red4(p0 + 4, g[4] * b.wx0, g[5] * b.wx0, g[6] * b.wx0, g[7] * b.wx0);
+  if (b.wx1 != 0.f) {
+    l4d_red4(p1, g[0] * b.wx1, g[1] * b.wx1, g[2] * b.wx1, g[3] * b.wx1);
+    l4d_red4(p1 + 4, g[4] * b.wx1, g[5] * b.wx1, g[6] * b.wx1, g[7] * b.wx1);
   }
 }
 
@@ -737,9 +790,15 @@ L4D_HD void l4d_gather_features(const DevModel& M, const L4DFrame& F, float x, f
         const float tau = qi == 0 ? F.cur.tau : (qi == 1 ? F.fwd.tau : F.bwd.tau);
         float v0[8], v1[8], v2[8], dummy[8];
         Bilerp b0 = l4d_bilerp(q0, R, tau, T), b1 = l4d_bilerp(q1, R, tau, T), b2 = l4d_bilerp(q2, R, tau, T);
-        l4d_plane_sample<false>(M.planes[s][2], R, b0, v0, dummy);
-        l4d_plane_sample<false>(M.planes[s][4], R, b1, v1, dummy);
-        l4d_plane_sample<false>(M.planes[s][5], R, b2, v2, dummy);
+        if (M.pl_con[s][0][0]) {        // contracted rows of this launch (k_contract_planes)
+          l4d_row_sample<false>(M.pl_con[s][0][qi], b0, v0, dummy);
+          l4d_row_sample<false>(M.pl_con[s][1][qi], b1, v1, dummy);
+          l4d_row_sample<false>(M.pl_con[s][2][qi], b2, v2, dummy);
+        } else {
+          l4d_plane_sample<false>(M.planes[s][2], R, b0, v0, dummy);
+          l4d_plane_sample<false>(M.planes[s][4], R, b1, v1, dummy);
+          l4d_plane_sample<false>(M.planes[s][5], R, b2, v2, dummy);
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) comb[c] = fmaf(wq, (v0[c] * v1[c]) * v2[c], comb[c]);
       }

@@ -24,6 +24,7 @@ struct GradWorkLayout {
   size_t att_w1t[2], att_w2t[2], att_w3[2];
   size_t flo_w0t, flo_w1t, flo_w2;
   size_t hd_comb[3], hf_comb;
+  size_t pl_rows;          // [query][scale][plane 2|4|5][R][8]
   size_t total;
 };
 
@@ -75,6 +76,23 @@ static inline StagedLayout staged_layout(const L4DConfig* c) {
   return L;
 }
 
+// floats of one full set of time-plane rows: [query 3][scale][plane 3][R][8]
+static inline size_t time_rows_floats(const L4DConfig* c) {
+  size_t n = 0;
+  for (uint32_t s = 0; s < c->n_plane_scales; ++s) n += (size_t)c->plane_res[s] * 8 * 3;
+  return 3 * n;
+}
+// the [scale][plane][query] pointer table over such a set at base (every row starts on a multiple of 32 bytes)
+template <class T>
+static inline void point_time_rows(const L4DConfig* c, T* base, T* (&tab)[L4D_MAX_PLANE_SCALES][3][3]) {
+  for (int q = 0; q < 3; ++q)
+    for (uint32_t s = 0; s < c->n_plane_scales; ++s)
+      for (int t = 0; t < 3; ++t) {
+        tab[s][t][q] = base;
+        base += (size_t)c->plane_res[s] * 8;
+      }
+}
+
 static inline GradWorkLayout grad_work_layout(const L4DConfig* c) {
   GradWorkLayout L;
   size_t o = 0;
@@ -98,6 +116,7 @@ static inline GradWorkLayout grad_work_layout(const L4DConfig* c) {
   L.flo_w2 = take(8 * 64 * f);
   for (int p = 0; p < 3; ++p) L.hd_comb[p] = take((size_t)c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels] * f);
   L.hf_comb = take((size_t)c->flow.offset[c->flow.n_levels] * 2 * f);
+  L.pl_rows = take(time_rows_floats(c) * f);
   L.total = o;
   return L;
 }
@@ -194,13 +213,14 @@ static inline void build_grads(const L4DConfig* c, const L4DMasterGrads* g, void
   if (comb) {
     for (int p = 0; p < 3; ++p) G.hd_comb[p] = F(L.hd_comb[p]);
     G.hf_comb = F(L.hf_comb);
+    point_time_rows(c, F(L.pl_rows), G.pl_rows);
   }
 }
 
 
 #define L4D_NT 128
 #define L4D_BWD_SCRATCH_CTAS 1024
-struct SavedLayout { size_t feat, flow_in, sigma, attr, hidden, flow, dfeat, dflow, tstart, hd_con, total; };
+struct SavedLayout { size_t feat, flow_in, sigma, attr, hidden, flow, dfeat, dflow, tstart, hd_con, pl_con, total; };
 static inline SavedLayout saved_layout(const L4DConfig* c, uint32_t n_rays, uint32_t S) {
   SavedLayout L;
   const size_t P = (size_t)n_rays * S;
@@ -223,18 +243,21 @@ static inline SavedLayout saved_layout(const L4DConfig* c, uint32_t n_rays, uint
   size_t dyn_entries = 0;
   for (int p = 0; p < 3; ++p) dyn_entries += c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels];
   L.hd_con = take(3 * dyn_entries * sizeof(float));
+  L.pl_con = take(time_rows_floats(c) * sizeof(float));      // contracted time-plane rows (DevModel::pl_con)
   L.total = o;
   return L;
 }
 // DevModel::hd_con inside the saved buffer of a launch (level offsets, hence plane sizes, are multiples of 8 entries)
-static inline void point_contracted(const L4DConfig* c, void* saved, uint32_t n_rays, uint32_t S, DevModel& M) {
+// mode bit 0: dynamic-hash tables, bit 1: time-plane rows
+static inline void point_contracted(const L4DConfig* c, void* saved, uint32_t n_rays, uint32_t S, DevModel& M, int mode) {
   SavedLayout L = saved_layout(c, n_rays, S);
   float* b = reinterpret_cast<float*>(reinterpret_cast<char*>(saved) + L.hd_con);
-  for (int q = 0; q < 3; ++q)
+  for (int q = 0; (mode & 1) && q < 3; ++q)
     for (int p = 0; p < 3; ++p) {
       M.hd_con[p][q] = b;
       b += c->hash_dynamic[p].offset[c->hash_dynamic[p].n_levels];
     }
+  if (mode & 2) point_time_rows<const float>(c, reinterpret_cast<const float*>(reinterpret_cast<char*>(saved) + L.pl_con), M.pl_con);
 }
 static inline SavedView saved_view(const L4DConfig* c, void* saved, uint32_t n_rays, uint32_t S) {
   SavedLayout L = saved_layout(c, n_rays, S);

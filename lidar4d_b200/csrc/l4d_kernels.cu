@@ -180,6 +180,55 @@ __global__ void k_contract_dynamic(const __grid_constant__ ContractArgs A) {
     }
   }
 }
+// DevModel::pl_con / DevGrads::pl_rows: the time (y) half of the bilinear blend of the three time planes of every scale is a
+// launch constant per query.  k_contract_planes blends the two live rows of a plane into one row per query before the gather;
+// k_fold_planes distributes the gradient rows over the two plane rows after the scatter, and clears them.
+struct TimeRowArgs {
+  float* plane[L4D_MAX_PLANE_SCALES][3];          // channels-last [T][R][8] plane (contract: read; fold: gradient, +=)
+  float* row[L4D_MAX_PLANE_SCALES][3][3];         // [scale][plane][query] rows [R][8]
+  uint32_t res[L4D_MAX_PLANE_SCALES];
+  uint32_t qmask;                                 // bit q: query q (cur, fwd, bwd) is live
+  int y0[3], y1[3];
+  float wy0[3], wy1[3];
+};
+static void fill_time_rows(TimeRowArgs& T, const L4DConfig* cfg, const L4DFrame* frame) {
+  memset(&T, 0, sizeof(T));
+  const L4DTimeQuery* qs[3] = {&frame->cur, &frame->fwd, &frame->bwd};
+  T.qmask = 1u | (frame->has_fwd ? 2u : 0u) | (frame->has_bwd ? 4u : 0u);
+  for (int q = 0; q < 3; ++q) {
+    const Bilerp b = l4d_bilerp(0.f, 2, qs[q]->tau, (int)cfg->time_resolution);
+    T.y0[q] = b.y0; T.y1[q] = b.y1; T.wy0[q] = b.wy0; T.wy1[q] = b.wy1;
+  }
+  for (uint32_t s = 0; s < cfg->n_plane_scales; ++s) T.res[s] = cfg->plane_res[s];
+}
+__global__ void k_contract_planes(const __grid_constant__ TimeRowArgs A) {
+  const uint32_t s = blockIdx.y / 3u, t = blockIdx.y % 3u;
+  const uint32_t R = A.res[s], n = R * 8u;
+  const float* P = A.plane[s][t];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (!((A.qmask >> q) & 1u)) continue;
+      A.row[s][t][q][i] = __ldg(P + (size_t)A.y0[q] * n + i) * A.wy0[q] + __ldg(P + (size_t)A.y1[q] * n + i) * A.wy1[q];
+    }
+  }
+}
+__global__ void k_fold_planes(const __grid_constant__ TimeRowArgs A) {
+  const uint32_t s = blockIdx.y / 3u, t = blockIdx.y % 3u;
+  const uint32_t R = A.res[s], n = R * 8u;
+  float* G = A.plane[s][t];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {       // one thread owns element i of all three queries: plain adds, no race
+      if (!((A.qmask >> q) & 1u)) continue;
+      const float v = A.row[s][t][q][i];
+      if (v == 0.f) continue;
+      G[(size_t)A.y0[q] * n + i] = fmaf(A.wy0[q], v, G[(size_t)A.y0[q] * n + i]);
+      if (A.wy1[q] != 0.f) G[(size_t)A.y1[q] * n + i] = fmaf(A.wy1[q], v, G[(size_t)A.y1[q] * n + i]);
+      A.row[s][t][q][i] = 0.f;
+    }
+  }
+}
 // flow grid: feature (2i + c) of an entry gets basis[i] * comb[entry][c] (DevGrads::hf_comb), then clear
 __global__ void k_fold_flow(float2* __restrict__ comb, float4* __restrict__ g, size_t n, float b0, float b1, float b2, float b3) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -807,7 +856,7 @@ __global__ void __launch_bounds__(NT) k_render_bwd(const __grid_constant__ BwdAr
       }
 
       // B4: encoders
-      l4d_bw_scatter(M, F, G, s);
+      l4d_bw_scatter<false>(M, F, G, s);
 
       // B5: flow MLP backprop + flow grid
       l4d_bw_flow_a(M, s, A.sv.flow_in + p, A.sv.P, s.dflow, xb, NT, ta_row, tb_row);
@@ -1069,6 +1118,14 @@ static int grid_for(K kernel, int nt, size_t smem, uint32_t work, int& grid, int
   return L4D_OK;
 }
 
+// Per-launch contraction of the time-dependent encoders with the frame's constants (split pipeline).  L4D_CONTRACT is an
+// A/B knob: bit 0 = dynamic-hash tables (DevModel::hd_con), bit 1 = time-plane rows (DevModel::pl_con, DevGrads::pl_rows);
+// 0 = gather / scatter on the parameters' own layouts as in round 1.
+static int contract_mode() {
+  static const char* e = getenv("L4D_CONTRACT");
+  static const int m = e ? atoi(e) & 3 : 3;
+  return m;
+}
 static void fill_split(SplitArgs& A, const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
                        void* saved) {
   memset(&A, 0, sizeof(A));
@@ -1123,10 +1180,10 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
   A.depth = depth; A.image = image; A.wsum = wsum; A.weights = weights; A.zvals = zvals;
   A.train = 1u;
   const size_t P = (size_t)rays->n_rays * rays->n_steps;
+  const int cmode = contract_mode();
+  point_contracted(cfg, saved, rays->n_rays, rays->n_steps, A.M, cmode);
   {
-    static const char* e = getenv("L4D_NO_CONTRACT");        // A/B knob: gather from the pair records as in round 1
-    if (!(e && atoi(e) != 0)) {
-      point_contracted(cfg, saved, rays->n_rays, rays->n_steps, A.M);
+    if (cmode & 1) {
       ContractArgs C;
       memset(&C, 0, sizeof(C));
       uint32_t nmax = 0;
@@ -1140,8 +1197,21 @@ extern "C" int l4d_render_forward(const L4DConfig* cfg, const void* staged, cons
       C.n_queries_mask = 1u | (frame->has_fwd ? 2u : 0u) | (frame->has_bwd ? 4u : 0u);
       C.q[0] = frame->cur; C.q[1] = frame->fwd; C.q[2] = frame->bwd;
       ++g_launches; k_contract_dynamic<<<dim3((unsigned)nblk(nmax), 3), 256, 0, st>>>(C);
-      prof_mark(st, "k_contract_dynamic");
     }
+    if (cmode & 2) {
+      TimeRowArgs T;
+      fill_time_rows(T, cfg, frame);
+      uint32_t rmax = 0;
+      for (uint32_t s2 = 0; s2 < cfg->n_plane_scales; ++s2) {
+        rmax = cfg->plane_res[s2] > rmax ? cfg->plane_res[s2] : rmax;
+        for (int t = 0; t < 3; ++t) {
+          T.plane[s2][t] = const_cast<float*>(A.M.planes[s2][t == 0 ? 2 : (t == 1 ? 4 : 5)]);
+          for (int q = 0; q < 3; ++q) T.row[s2][t][q] = const_cast<float*>(A.M.pl_con[s2][t][q]);
+        }
+      }
+      ++g_launches; k_contract_planes<<<dim3((unsigned)nblk((size_t)rmax * 8), 3 * cfg->n_plane_scales), 256, 0, st>>>(T);
+    }
+    if (cmode) prof_mark(st, "k_contract");
   }
   if (cfg->mlp_fp16) {
     {
@@ -1225,6 +1295,8 @@ extern "C" int l4d_render_backward_ex(const L4DConfig* cfg, const void* staged, 
     SplitArgs A;
     fill_split(A, cfg, staged, frame, rays, const_cast<void*>(saved));
     build_grads(cfg, grads, grad_work, A.G, true);
+    const bool rows = (contract_mode() & 2) != 0;        // the forward of this launch left the contracted time planes in `saved`
+    if (rows) point_contracted(cfg, const_cast<void*>(saved), rays->n_rays, rays->n_steps, A.M, 2);
     A.g_depth = g_depth; A.g_image = g_image; A.g_wsum = g_wsum; A.g_weights = g_weights;
     A.train = 1u;
     const size_t P = (size_t)rays->n_rays * rays->n_steps;
@@ -1263,10 +1335,29 @@ extern "C" int l4d_render_backward_ex(const L4DConfig* cfg, const void* staged, 
           ++g_launches; k_bwd_scatter<L4D_NT, L4D_SC_STATIC_PLANES | L4D_SC_DYNAMIC_HASH, L4D_SCATTER_S_CTAS><<<grid, L4D_NT, 0, st>>>(A);
           prof_mark(st, "k_bwd_scatter_sd");
         } else {
-          rc = grid_for(k_bwd_scatter<L4D_NT, L4D_SC_ALL, L4D_SCATTER_MIN_CTAS>, L4D_NT, 0, tiles, grid);
-          if (rc != L4D_OK) return rc;
-          ++g_launches; k_bwd_scatter<L4D_NT, L4D_SC_ALL, L4D_SCATTER_MIN_CTAS><<<grid, L4D_NT, 0, st>>>(A);
+          if (rows) {
+            rc = grid_for(k_bwd_scatter<L4D_NT, L4D_SC_ALL, L4D_SCATTER_MIN_CTAS, true>, L4D_NT, 0, tiles, grid);
+            if (rc != L4D_OK) return rc;
+            ++g_launches; k_bwd_scatter<L4D_NT, L4D_SC_ALL, L4D_SCATTER_MIN_CTAS, true><<<grid, L4D_NT, 0, st>>>(A);
+          } else {
+            rc = grid_for(k_bwd_scatter<L4D_NT, L4D_SC_ALL, L4D_SCATTER_MIN_CTAS>, L4D_NT, 0, tiles, grid);
+            if (rc != L4D_OK) return rc;
+            ++g_launches; k_bwd_scatter<L4D_NT, L4D_SC_ALL, L4D_SCATTER_MIN_CTAS><<<grid, L4D_NT, 0, st>>>(A);
+          }
           prof_mark(st, "k_bwd_scatter");
+        }
+        if (rows && !split) {       // gradient rows -> the two live time rows of every time plane
+          TimeRowArgs T;
+          fill_time_rows(T, cfg, frame);
+          uint32_t rmax = 0;
+          for (uint32_t s2 = 0; s2 < cfg->n_plane_scales; ++s2) {
+            rmax = cfg->plane_res[s2] > rmax ? cfg->plane_res[s2] : rmax;
+            for (int t = 0; t < 3; ++t) {
+              T.plane[s2][t] = A.G.planes_cl[s2][t == 0 ? 2 : (t == 1 ? 4 : 5)];
+              for (int q = 0; q < 3; ++q) T.row[s2][t][q] = A.G.pl_rows[s2][t][q];
+            }
+          }
+          ++g_launches; k_fold_planes<<<dim3((unsigned)nblk((size_t)rmax * 8), 3 * cfg->n_plane_scales), 256, 0, st>>>(T);
         }
       }
       rc = grid_for(k_bwd_scatter_static<L4D_NT>, L4D_NT, 0, tiles, grid);

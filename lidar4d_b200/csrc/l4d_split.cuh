@@ -36,11 +36,12 @@ struct SplitArgs {
 // FLOW_GIVEN: the flow was already written by k_fwd_flow_tc; then this kernel has no MLP at all.
 // TILE: features go out as the fp16 hi|lo operand tiles of the tensor-core dense kernels (SavedView::feat_tc);
 // the sample space is then walked in whole 128-row tiles so the rows past the end of a ray get zeros.
-// Occupancy of the MLP-free variant, measured at L=16 (ms per 8192 rays): 3 CTAs/SM 12.8, 4: 11.2, 5: 10.2, 6: 9.9,
-// 7: 10.6, 8: 10.7 -> 6 (80 registers, 24 B of spills).  The variant that also runs the flow MLP keeps 64
-// accumulators live and stays at 4.
+// Occupancy of the MLP-free variant, measured at L=16: round 1 (pair-record gathers, ms per 8192 rays): 3 CTAs/SM 12.8, 4: 11.2,
+// 5: 10.2, 6: 9.9, 7: 10.6, 8: 10.7.  Round 2 (contracted dynamic tables: 4-byte gathers, a tenth of the arithmetic; ms per
+// 16,384 rays): 6: 17.7, 8: 16.4 (64 registers, 168 B of spills), 10: 18.1, 12: 20.7 -> 8.  The variant that also runs the flow
+// MLP keeps 64 accumulators live and stays at 4.
 #ifndef L4D_GATHER_MIN_CTAS
-#define L4D_GATHER_MIN_CTAS 6
+#define L4D_GATHER_MIN_CTAS 8
 #endif
 template <int NT, bool FLOW_GIVEN, bool TILE>
 __global__ void __launch_bounds__(NT, FLOW_GIVEN ? L4D_GATHER_MIN_CTAS : 4) k_fwd_gather(const __grid_constant__ SplitArgs A) {
@@ -299,10 +300,11 @@ __global__ void __launch_bounds__(NT) k_bwd_dense(const __grid_constant__ SplitA
 // -------------------------------------------------------------------------------------------
 // backward 2/3: scatter dL/dfeature through the encoders (vector REDs), thread == sample.
 // -------------------------------------------------------------------------------------------
-// 3 CTAs/SM = 168 registers: almost no spills.  At 4 (128 registers) the 220 B of spill traffic per thread competes
-// with the REDs / gathers / shuffles for the LSU pipe that bounds this kernel (measured 12.8 -> 11.8 ms).
+// Round 1: 3 CTAs/SM = 168 registers, almost no spills; at 4 (128 registers) 220 B of spill traffic per thread competed with the
+// REDs / gathers / shuffles for the LSU pipe (12.8 vs 11.8 ms).  Round 2: with the time planes read and reduced as contracted
+// rows the kernel spills 76 B at 128 registers, and 4 CTAs/SM win: 17.9 vs 19.4 ms (3) and 19.3 ms (5) per 16,384 rays.
 #ifndef L4D_SCATTER_MIN_CTAS
-#define L4D_SCATTER_MIN_CTAS 3
+#define L4D_SCATTER_MIN_CTAS 4
 #endif
 #ifndef L4D_SCATTER_T_CTAS       // time-plane kernel
 #define L4D_SCATTER_T_CTAS 3
@@ -322,7 +324,7 @@ struct DfeatFromTile {
 
 // PARTS selects the sinks (l4d_bwd.cuh).  Default = all of them in one kernel; the two-kernel variant (time planes, which
 // need the flow and produce dL/dflow | static planes + dynamic hash at 4 CTAs/SM) is an A/B option that measured slower.
-template <int NT, int PARTS, int MIN_CTAS>
+template <int NT, int PARTS, int MIN_CTAS, bool ROWS = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) k_bwd_scatter(const __grid_constant__ SplitArgs A) {
   const DevModel& M = A.M;
   const size_t P = A.sv.P;
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) k_bwd_scatter(const __grid_const
 #pragma unroll
     for (int k = 0; k < 6; ++k) flow[k] = (PARTS & L4D_SC_TIME_PLANES) ? A.sv.flow[(size_t)k * P + p] : 0.f;
     DfeatFromTile df{A.sv.dfeat + l4d_dfeat_off(A.sv, ray, j), active};
-    l4d_bw_scatter_t<true, DfeatFromTile, false, PARTS>(M, A.F, A.G, x, y, z, flow, df, dflow, active);
+    l4d_bw_scatter_t<true, DfeatFromTile, false, PARTS, ROWS>(M, A.F, A.G, x, y, z, flow, df, dflow, active);
     if (active && (PARTS & L4D_SC_TIME_PLANES)) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) A.sv.dflow[(size_t)k * P + p] = dflow[k];

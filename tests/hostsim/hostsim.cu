@@ -121,6 +121,39 @@ extern "C" int hs_unstage_grads(const L4DConfig* cfg, const void* grad_work, con
   return L4D_OK;
 }
 
+// ---- host mirror of k_contract_dynamic / k_contract_planes: fills `store`, points M.hd_con / M.pl_con at it ----------
+static void contract_for_frame(const L4DConfig* cfg, const L4DFrame* frame, DevModel& M, std::vector<float>& store) {
+  size_t tot = 0;
+  for (int p = 0; p < 3; ++p) tot += M.hd_slice_entries[p];
+  store.assign(3 * tot + time_rows_floats(cfg), 0.f);
+  float* b = store.data();
+  const L4DTimeQuery* qs[3] = {&frame->cur, &frame->fwd, &frame->bwd};
+  const bool live[3] = {true, frame->has_fwd != 0, frame->has_bwd != 0};
+  for (int q = 0; q < 3; ++q)
+    for (int p = 0; p < 3; ++p) {
+      const uint32_t n = M.hd_slice_entries[p];
+      M.hd_con[p][q] = b;
+      if (live[q]) {
+        const uint4* tab = reinterpret_cast<const uint4*>(M.hd[p]) + (size_t)l4d_time_pair(*qs[q], cfg->time_resolution) * n;
+        for (uint32_t e = 0; e < n; ++e) b[e] = l4d_contract_entry(tab[e], *qs[q], cfg->time_resolution);
+      }
+      b += n;
+    }
+  float* rows[L4D_MAX_PLANE_SCALES][3][3];
+  point_time_rows(cfg, b, rows);
+  for (uint32_t s = 0; s < cfg->n_plane_scales; ++s)
+    for (int t = 0; t < 3; ++t)
+      for (int q = 0; q < 3; ++q) {
+        M.pl_con[s][t][q] = rows[s][t][q];
+        if (!live[q]) continue;
+        const int R = (int)cfg->plane_res[s];
+        const Bilerp bl = l4d_bilerp(0.f, 2, qs[q]->tau, (int)cfg->time_resolution);
+        const float* P = M.planes[s][t == 0 ? 2 : (t == 1 ? 4 : 5)];
+        for (int x = 0; x < R; ++x)
+          for (int c = 0; c < 8; ++c) rows[s][t][q][x * 8 + c] = l4d_contract_texel(P, R, bl, x, c);
+      }
+}
+
 // ---- forward (mirror of k_render_fwd) ---------------------------------------------------
 extern "C" int hs_render_forward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame, const L4DRays* rays,
                                  float* depth, float* image, float* wsum, float* weights, float* zvals, void* saved) {
@@ -133,27 +166,10 @@ extern "C" int hs_render_forward(const L4DConfig* cfg, const void* staged, const
   SavedView sv;
   memset(&sv, 0, sizeof(sv));
   if (saved) sv = saved_view(cfg, saved, rays->n_rays, S);
-  // rays->reserved bit 2 (host-sim only): gather the dynamic hash from the per-launch contracted tables, built here the way
-  // k_contract_dynamic builds them (DevModel::hd_con)
+  // rays->reserved bit 2 (host-sim only): gather the dynamic hash and the time planes from the per-launch contracted
+  // tables / rows (DevModel::hd_con, pl_con)
   std::vector<float> con_store;
-  if (rays->reserved & 4u) {
-    size_t tot = 0;
-    for (int p = 0; p < 3; ++p) tot += M.hd_slice_entries[p];
-    con_store.assign(3 * tot, 0.f);
-    float* b = con_store.data();
-    const L4DTimeQuery* qs[3] = {&frame->cur, &frame->fwd, &frame->bwd};
-    const bool live[3] = {true, frame->has_fwd != 0, frame->has_bwd != 0};
-    for (int q = 0; q < 3; ++q)
-      for (int p = 0; p < 3; ++p) {
-        const uint32_t n = M.hd_slice_entries[p];
-        M.hd_con[p][q] = b;
-        if (live[q]) {
-          const uint4* tab = reinterpret_cast<const uint4*>(M.hd[p]) + (size_t)l4d_time_pair(*qs[q], cfg->time_resolution) * n;
-          for (uint32_t e = 0; e < n; ++e) b[e] = l4d_contract_entry(tab[e], *qs[q], cfg->time_resolution);
-        }
-        b += n;
-      }
-  }
+  if (rays->reserved & 4u) contract_for_frame(cfg, frame, M, con_store);
   const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, S, rays->perturb, rays->seed);
   for (uint32_t ray = 0; ray < rays->n_rays; ++ray) {
     const float* o = rays->rays_o + 3 * ray;
@@ -219,6 +235,8 @@ extern "C" int hs_render_backward(const L4DConfig* cfg, const void* staged, cons
   // (DevGrads::hd_comb) and fold them afterwards exactly like k_fold_dynamic does
   const bool comb = (rays->reserved & 2u) != 0;
   build_grads(cfg, grads, grad_work, G, comb);
+  std::vector<float> con_store;          // comb also runs the time planes through the contracted rows + gradient rows + fold
+  if (comb) { contract_for_frame(cfg, frame, M, con_store); for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) M.hd_con[p][q] = nullptr; }
   if (comb) G.hf_comb = nullptr;          // the flow-grid accumulator belongs to k_bwd_flowgrid (no host mirror)
   const L4DFrame& F = *frame;
   const uint32_t S = rays->n_steps;
@@ -297,7 +315,7 @@ extern "C" int hs_render_backward(const L4DConfig* cfg, const void* staged, cons
         const int rows = std::min(64, (int)M.sigma_in_pad - c * 64);
         outer_accum(TA.data(), TB.data(), NT, rows, G.sig_w1t + (size_t)c * 64 * 64);
       }
-      for (int m = 0; m < NT; ++m) l4d_bw_scatter(M, F, G, st[m]);
+      for (int m = 0; m < NT; ++m) { if (comb) l4d_bw_scatter<true>(M, F, G, st[m]); else l4d_bw_scatter<false>(M, F, G, st[m]); }
       for (int m = 0; m < NT; ++m) l4d_bw_flow_a(M, st[m], sv.flow_in + P(m), sv.P, st[m].dflow, XB(m), 1, TAR(m), TBR(m));
       outer_accum(TA.data(), TB.data(), NT, 8, G.flo_w2);
       for (int m = 0; m < NT; ++m) l4d_bw_flow_b(M, st[m], st[m].dflow, XB(m), 1, TAR(m), TBR(m));
@@ -312,6 +330,27 @@ extern "C" int hs_render_backward(const L4DConfig* cfg, const void* staged, cons
           if (r < L4D_ENC) G.att_w1t[net][(size_t)r * 64 + j] += enc[r] * cs;
           else G.att_w1t[net][(size_t)(M.attr_in_dim + (r - L4D_ENC)) * 64 + j] += cs;
         }
+  }
+  if (comb) {          // mirror of k_fold_planes (l4d_kernels.cu)
+    const L4DTimeQuery* qs[3] = {&frame->cur, &frame->fwd, &frame->bwd};
+    const bool live[3] = {true, frame->has_fwd != 0, frame->has_bwd != 0};
+    for (uint32_t s = 0; s < cfg->n_plane_scales; ++s)
+      for (int t = 0; t < 3; ++t) {
+        const int R = (int)cfg->plane_res[s];
+        float* Gp = G.planes_cl[s][t == 0 ? 2 : (t == 1 ? 4 : 5)];
+        for (int q = 0; q < 3; ++q) {
+          if (!live[q]) continue;
+          const Bilerp bl = l4d_bilerp(0.f, 2, qs[q]->tau, (int)cfg->time_resolution);
+          float* row = G.pl_rows[s][t][q];
+          for (int i = 0; i < R * 8; ++i) {
+            const float v = row[i];
+            if (v == 0.f) continue;
+            Gp[(size_t)bl.y0 * R * 8 + i] = fmaf(bl.wy0, v, Gp[(size_t)bl.y0 * R * 8 + i]);
+            if (bl.wy1 != 0.f) Gp[(size_t)bl.y1 * R * 8 + i] = fmaf(bl.wy1, v, Gp[(size_t)bl.y1 * R * 8 + i]);
+            row[i] = 0.f;
+          }
+        }
+      }
   }
   if (comb) {          // mirror of k_fold_dynamic (l4d_kernels.cu)
     const bool single = F.cur.single != 0;

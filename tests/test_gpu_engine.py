@@ -207,7 +207,8 @@ def test_launch_counter_counts_kernels(dev):
     with torch.no_grad():
         _render(m, dev)
     n1 = m.gpu_launches
-    assert 3 <= n1 - n0 <= 40              # staging (first call) + flow / gather / dense
+    assert 5 <= n1 - n0 <= 42              # staging (first call) + contraction / flow / gather / dense
     with torch.no_grad():
         _render(m, dev)
-    assert m.gpu_launches - n1 == 3        # k_fwd_flow_tc, k_fwd_gather, k_fwd_dense_tc
+    # k_contract_dynamic, k_contract_planes, k_fwd_flow_tc, k_fwd_gather, k_fwd_dense_tc
+    assert m.gpu_launches - n1 == 5
