@@ -87,7 +87,9 @@ def kernel_bytes(cfg):
     """Algorithmic bytes per sample of every kernel of the pipeline."""
     L, D = cfg.n_levels_hash, cfg.sigma_in_dim
     planes = 4 * 3 * 4 * 32
-    gather = L * 8 * 8 + 3 * (3 * 2 * L * 4 * 8) + 8 * 8 * 16 + planes * 4
+    # gather: static hash 8 B x 8 corners; dynamic hash from the per-launch contracted tables: 4 B x 4 corners x 3 planes x 3 queries
+    # (round 1: 16-byte pair records); flow grid; static planes 4 texels, time planes 2 texels of a contracted row x 3 queries
+    gather = L * 8 * 8 + 3 * 3 * L * 4 * 4 + 8 * 8 * 16 + 4 * 3 * (4 * 32) + 4 * 3 * 3 * (2 * 32)
     fwd, bwd = algorithmic_bytes(cfg)
     exch = 4 * (D + 16 + 6)
     return {
@@ -96,7 +98,9 @@ def kernel_bytes(cfg):
         "k_fwd_flow": 8 * 8 * 16 + 4 * 22,                                 # flow-grid gather + flow-in / flow planes written
         "k_fwd_dense": 4 * D + 12,                                          # features read, sigma/attr saved
         "k_bwd_dense": 2 * 4 * D + 4 * D + 12,                              # features read twice, dfeat written
-        "k_bwd_scatter": 2 * (3 * 2 * L * 4 * 16 + 4 * planes) + 4 * planes + 4 * (D - 4 * L) + 48,
+        # dynamic hash: one fp32 per entry read-modify-written (scalar accumulators); plane gradients (static 4 texels, time rows
+        # 2 texels x 3 queries) read-modify-written + the same texels read for the product rule; dfeat read, dflow written
+        "k_bwd_scatter": 2 * (3 * L * 4 * 4 + 4 * 3 * 4 * 32 + 4 * 3 * 3 * 2 * 32) + (4 * 3 * 4 * 32 + 4 * 3 * 3 * 2 * 32) + 4 * (D - 4 * L) + 48,
         "k_bwd_scatter_static": 2 * (L * 8 * 16) + 4 * 4 * L,
         "k_bwd_flow": 4 * 22 + 4 * 16,                                       # dflow + flow-in read, dfin written
         "k_bwd_flowgrid": 2 * (8 * 8 * 32) + 4 * 16,
@@ -284,11 +288,36 @@ def workload_config(args, note=None):
 # =============================================================================
 # GPU arm
 # =============================================================================
-def red_counts(cfg):
-    """Vector reductions (RED.E.ADD.F32x4 lane-ops) per sample of the kernels whose ceiling is the L2 atomic unit
-    (one per hash corner; DESIGN.md 4.2 'atomic floor')."""
+STATIC_AGG_RES = 1200        # L4D_STATIC_AGG_RES of lidar4d_b200/csrc/l4d_split.cuh (levels whose runs of equal cells are summed in the warp)
+
+
+def red_counts(cfg, rays=None):
+    """Vector reductions (RED.E.ADD.F32x4 lane-ops) per sample that k_bwd_scatter_static EXECUTES - the kernel whose ceiling is
+    the L2 atomic unit (DESIGN.md 4.2 'atomic floor').  Algorithmically it is one per hash corner (8 L); at the levels up to
+    res 1200 the kernel sums every run of consecutive samples of a warp that share their cell and issues the 8 corners once per
+    run, so the executed count is 8 x runs / samples there: the run statistics are computed here, on the host, from the
+    benchmark's own rays (unjittered z grid), the same way the kernel forms its runs (32 consecutive samples of a ray)."""
     L = cfg.n_levels_hash
-    return {"k_bwd_scatter_static": L * 8}
+    g = cfg.static_grid()
+    out = {"k_bwd_scatter_static": float(L * 8), "k_bwd_scatter_static_algorithmic": float(L * 8)}
+    if rays is None:
+        return out
+    ro, rd = rays
+    ro, rd = np.asarray(ro, np.float32)[:256], np.asarray(rd, np.float32)[:256]
+    z = np.linspace(np.float32(cfg.near_lidar), np.float32(cfg.far_lidar), S_STEPS, dtype=np.float32)
+    x01 = (ro[:, None, :] + rd[:, None, :] * z[None, :, None] + np.float32(cfg.bound)) / np.float32(2 * cfg.bound)   # [rays, S, 3]
+    executed = 0.0
+    for l in range(L):
+        if int(g.resolution[l]) > STATIC_AGG_RES:
+            executed += 8.0
+            continue
+        cell = np.floor(x01 * g.scale[l] + np.float32(0.5)).astype(np.int64)
+        key = cell[..., 0] + int(g.resolution[l]) * (cell[..., 1] + int(g.resolution[l]) * cell[..., 2])      # [rays, S]
+        key = key.reshape(key.shape[0], -1, 32)                      # warps of 32 consecutive samples (S is a multiple of 32)
+        runs = 1 + (key[..., 1:] != key[..., :-1]).sum(-1)           # runs per warp
+        executed += 8.0 * float(runs.sum()) / float(key.size)
+    out["k_bwd_scatter_static"] = executed
+    return out
 
 
 def micro_peaks():
@@ -569,7 +598,7 @@ def run_b200(args):
     peak, peak_src = peaks()
     samples_per_launch = min(rb, n_rays) * S_STEPS if not infer else min(model.infer_ray_chunk, n_rays) * S_STEPS
     kbytes = kernel_bytes(model.cfg)
-    reds = red_counts(model.cfg)
+    reds = red_counts(model.cfg, (frames[0][0].numpy(), frames[0][1].numpy()) if S_STEPS % 32 == 0 else None)
     mp = micro_peaks()
     nb = ncu_binding()
     nbk = nb.get("kernels", {})
@@ -582,7 +611,10 @@ def run_b200(args):
         if name in reds and mp.get("red128_glaneops_s"):
             rate = reds[name] * samples_per_launch / (avg * 1e-3) / 1e9
             k["binding"] = {"unit": "L2 atomic unit: G RED.128 lane-ops/s", "achieved": rate, "peak": mp["red128_glaneops_s"],
-                            "frac": rate / mp["red128_glaneops_s"], "source": "live duration x algorithmic REDs vs scripts/micro/red_bench.cu (profiles/r02_micro_peaks.json)"}
+                            "frac": rate / mp["red128_glaneops_s"], "red_lane_ops_per_sample_executed": reds[name],
+                            "red_lane_ops_per_sample_algorithmic": reds.get(name + "_algorithmic"),
+                            "source": "live duration x executed REDs (8 per level, 8 x runs/samples at the warp-aggregated levels: host-side run "
+                                      "statistics of the benchmark's rays) vs scripts/micro/red_bench.cu (profiles/r02_micro_peaks.json)"}
         elif name in nbk and nbk[name].get("limiter_pct") is not None:
             k["binding"] = {"unit": nbk[name]["limiter_unit"], "frac": nbk[name]["limiter_pct"] / 100.0,
                             "achieved": nbk[name]["limiter_pct"], "peak": 100.0, "achieved_unit": "% of the unit's peak rate (ncu)",

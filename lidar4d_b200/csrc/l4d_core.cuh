@@ -362,8 +362,8 @@ L4D_HD float l4d_contract_entry(uint4 rec, const L4DTimeQuery& q, uint32_t n_sli
 //   0  one 16-byte load of the aligned quad of entries that holds the first x-corner (the second x-corner is in the same
 //      quad three times out of four) + a conditional 4-byte load otherwise: 2.5 instead of 4 sector requests per level, but
 //      a divergent branch per row - 25.8 ms: the loads of a level no longer overlap
-//   1  four independent 4-byte loads (no branch, no selects)
-//   2  the quad load + an unconditional 4-byte load of the second x-corner
+//   1  four independent 4-byte loads (no branch, no selects) - 17.7 ms (16.4 ms at 8 CTAs/SM): the default
+//   2  the quad load + an unconditional 4-byte load of the second x-corner - 23.5 ms
 #ifndef L4D_CON_GATHER
 #define L4D_CON_GATHER 1
 #endif
@@ -380,11 +380,12 @@ L4D_HD float l4d_encode2_con(const DevGrid& g, const float* con, int l, float x,
   for (int r = 0; r < 2; ++r) {
     const uint32_t i0 = idx[2 * r], i1 = idx[2 * r + 1];
     const float4 q = l4d_ld4(base + (i0 & ~3u));
-    const uint32_t s0 = i0 & 3u, s1 = i1 & 3u;
+    const uint32_t s0 = i0 & 3u;
     const float v0 = s0 == 0u ? q.x : (s0 == 1u ? q.y : (s0 == 2u ? q.z : q.w));
 #if L4D_CON_GATHER == 2
     const float v1 = l4d_ld1(base + i1);
 #else
+    const uint32_t s1 = i1 & 3u;
     float v1 = s1 == 0u ? q.x : (s1 == 1u ? q.y : (s1 == 2u ? q.z : q.w));
     if ((i0 >> 2) != (i1 >> 2)) v1 = l4d_ld1(base + i1);
 #endif

@@ -470,8 +470,15 @@ __global__ void __launch_bounds__(NT, 4) k_bwd_flowgrid(const __grid_constant__ 
 // (ncu: 31 GB of DRAM traffic, L2 hit 59 %).  Here every CTA sweeps the samples once per level, so the whole
 // chip works on one level at a time and its gradient slab stays L2-resident.
 // -------------------------------------------------------------------------------------------
+// L4D_STATIC_AGG_RES (0 = off): at the coarsest levels consecutive samples of a ray share their cell for 2-4 samples (res 512-1200
+// vs ~215 cells along a ray); their 8 x 4 corner values are summed with a segmented warp scan and only the last lane of a run
+// issues the REDs.  The kernel is bound by the L2 atomic rate (96 % of the measured ceiling), the scans are free:
+// 8.93 -> 7.50 ms per 16,384 rays at L = 16 with the four levels up to res 1200 (profiles/r02_v8_ab_contract.txt).
+#ifndef L4D_STATIC_AGG_RES
+#define L4D_STATIC_AGG_RES 1200
+#endif
 template <int NT>
-__global__ void __launch_bounds__(NT, 8) k_bwd_scatter_static(const __grid_constant__ SplitArgs A) {
+__global__ void __launch_bounds__(NT, L4D_STATIC_AGG_RES ? 5 : 8) k_bwd_scatter_static(const __grid_constant__ SplitArgs A) {
   const DevModel& M = A.M;
   const size_t P = A.sv.P;
   const RaySampling rs = l4d_make_sampling(M.near_lidar, M.far_lidar, A.S, A.perturb, A.seed);
@@ -481,18 +488,50 @@ __global__ void __launch_bounds__(NT, 8) k_bwd_scatter_static(const __grid_const
   for (int l = 0; l < L; ++l) {
     float* gbase = A.G.hs + (size_t)M.gs.offset[l] * 4;
     const size_t dk = l4d_dfeat_k(row_hash_s + 4 * l);     // row_hash_s is a multiple of 16: one float4 per level
-    for (size_t p = (size_t)blockIdx.x * NT + threadIdx.x; p < P; p += (size_t)gridDim.x * NT) {
+    const bool agg = L4D_STATIC_AGG_RES && M.gs.res[l] <= (uint32_t)L4D_STATIC_AGG_RES;      // warp-uniform
+    for (size_t base = (size_t)blockIdx.x * NT; base < P; base += (size_t)gridDim.x * NT) {
+      // whole warps stay together (the aggregated levels shuffle); lanes past the end shadow the last sample with zero gradient
+      const size_t pp = base + threadIdx.x;
+      const bool active = pp < P;
+      const size_t p = active ? pp : P - 1;
       const uint32_t ray = (uint32_t)(p / A.S), j = (uint32_t)(p % A.S);
-      const float4 dd = __ldg(reinterpret_cast<const float4*>(A.sv.dfeat + l4d_dfeat_off(A.sv, ray, j) + dk));
-      const float d0 = dd.x, d1 = dd.y, d2 = dd.z, d3 = dd.w;
+      float4 dd = __ldg(reinterpret_cast<const float4*>(A.sv.dfeat + l4d_dfeat_off(A.sv, ray, j) + dk));
+      if (!active) dd = make_float4(0.f, 0.f, 0.f, 0.f);
       const float zj = l4d_z(rs, A.ray_offset + ray, j);
       const float x = l4d_x01(__ldg(A.rays_o + 3 * ray), __ldg(A.rays_d + 3 * ray), zj, M.bound);
       const float y = l4d_x01(__ldg(A.rays_o + 3 * ray + 1), __ldg(A.rays_d + 3 * ray + 1), zj, M.bound);
       const float z = l4d_x01(__ldg(A.rays_o + 3 * ray + 2), __ldg(A.rays_d + 3 * ray + 2), zj, M.bound);
       uint32_t idx[8]; float w[8];
       l4d_corners3(M.gs, l, x, y, z, idx, w);
+#if L4D_STATIC_AGG_RES
+      if (agg) {
+        uint32_t cx, cy, cz; float fx, fy, fz;
+        const float sc = M.gs.scale[l];
+        l4d_pos_fract(sc, x, cx, fx); l4d_pos_fract(sc, y, cy, fy); l4d_pos_fract(sc, z, cz, fz);
+        // equal keys <=> equal cells for neighbouring lanes (their linear cell indices differ by far less than 2^32)
+        const WarpRuns r = l4d_warp_runs((int)(cx + M.gs.res[l] * (cy + M.gs.res[l] * cz)));
 #pragma unroll
-      for (int c = 0; c < 8; ++c) l4d_red4(gbase + (size_t)idx[c] * 4, w[c] * d0, w[c] * d1, w[c] * d2, w[c] * d3);
+        for (int h = 0; h < 2; ++h) {        // two passes of 4 corners x 4 features keep 16 values live
+          float s0[8], s1[8];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            s0[2 * c] = w[4 * h + c] * dd.x; s0[2 * c + 1] = w[4 * h + c] * dd.y;
+            s1[2 * c] = w[4 * h + c] * dd.z; s1[2 * c + 1] = w[4 * h + c] * dd.w;
+          }
+          l4d_seg_sum8(s0, r);
+          l4d_seg_sum8(s1, r);
+          if (r.tail) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) l4d_red4(gbase + (size_t)idx[4 * h + c] * 4, s0[2 * c], s0[2 * c + 1], s1[2 * c], s1[2 * c + 1]);
+          }
+        }
+        continue;
+      }
+#endif
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) l4d_red4(gbase + (size_t)idx[c] * 4, w[c] * dd.x, w[c] * dd.y, w[c] * dd.z, w[c] * dd.w);
+      }
     }
   }
 }
