@@ -615,18 +615,22 @@ def run_b200(args):
                             "red_lane_ops_per_sample_algorithmic": reds.get(name + "_algorithmic"),
                             "source": "live duration x executed REDs (8 per level, 8 x runs/samples at the warp-aggregated levels: host-side run "
                                       "statistics of the benchmark's rays) vs scripts/micro/red_bench.cu (profiles/r02_micro_peaks.json)"}
+        elif name in nb.get("stale", {}):
+            # the committed ncu capture predates this kernel's current code: name the unit it was bound by then, claim no fraction
+            k["binding"] = {"unit": nbk.get(name, {}).get("limiter_unit"), "frac": None, "achieved": None, "peak": None,
+                            "stale": nb["stale"][name], "last_capture": nbk.get(name, {}).get("limiter")}
         elif name in nbk and nbk[name].get("limiter_pct") is not None:
             k["binding"] = {"unit": nbk[name]["limiter_unit"], "frac": nbk[name]["limiter_pct"] / 100.0,
                             "achieved": nbk[name]["limiter_pct"], "peak": 100.0, "achieved_unit": "% of the unit's peak rate (ncu)",
                             "source": f"ncu --set full capture of this kernel ({nb.get('source')}): the profiler's own achieved/peak ratio of the busiest unit"}
-        if name in nbk:
+        if name in nbk and name not in nb.get("stale", {}):
             k["ncu"] = nbk[name]
         kern[name] = k
     dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
     traffic = None
     try:        # dram__bytes_read+write of the dominant kernel from the committed ncu capture (scaled to this launch size)
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if args.levels == 16 and tj["dram_bytes_per_launch"].get(dom) is not None:
+        if args.levels == 16 and tj["dram_bytes_per_launch"].get(dom) is not None and dom not in nb.get("stale", {}):
             traffic = tj["dram_bytes_per_launch"][dom] * (samples_per_launch / (float(tj.get("rays_per_launch", 8192)) * S_STEPS))
     except Exception:
         traffic = None
