@@ -48,6 +48,16 @@ def test_argument_errors_are_codes_not_crashes():
     bad.sigma_in_dim = 7
     assert lib.l4d_staged_bytes(C.byref(bad)) == 0
     assert b"sigma_in_dim" in lib.l4d_last_error()
+    # the scalar per-entry accumulators / contracted tables of the dynamic hash are addressed as aligned quads of entries
+    odd = _capi.make_config(FieldConfig())
+    odd.hash_dynamic[1].offset[3] += 4
+    assert lib.l4d_saved_bytes(C.byref(odd), 16, 768) == 0
+    assert b"multiples of 8" in lib.l4d_last_error()
+    # the saved buffer of a launch carries the contracted dynamic tables (3 queries x entries x 4 B) and time-plane rows
+    c16 = FieldConfig(n_levels_hash=16)
+    n_dyn = sum(int(c16.dynamic_grid(p).offset[-1]) for p in range(3))
+    small, big = lib.l4d_saved_bytes(C.byref(_capi.make_config(c16)), 1, 1), 3 * n_dyn * 4
+    assert small > big + 3 * 3 * 8 * 4 * sum(c16.min_resolution * m for m in c16.plane_scales)
     fr = _capi.make_frame_struct(make_frame(0.3, 51, 8))
     rays = _capi.L4DRays()
     rc = lib.l4d_render_forward(C.byref(cfg), None, C.byref(fr), C.byref(rays), None, None, None, None, None, None, 0, None)

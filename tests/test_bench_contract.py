@@ -32,3 +32,26 @@ def test_gpu_arm_fails_loudly_without_cuda():
     r = _run({"RANK": "0", "WORLD_SIZE": "1"}, "--steps", "1", "--warmup", "1", "--no-cpu-baseline")
     assert r.returncode != 0
     assert "needs a GPU" in (r.stderr + r.stdout)
+
+
+def test_executed_red_count_of_the_static_scatter():
+    """bench.py's RED-rate binding of k_bwd_scatter_static uses the reductions the kernel EXECUTES: 8 per level, and at the
+    warp-aggregated levels 8 per run of consecutive samples that share a cell (host-side run statistics of the rays)."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    from lidar4d_b200.geometry import FieldConfig
+    from lidar4d_b200.rays import synthetic_sweep
+    cfg = FieldConfig(**bench.model_kwargs(16))
+    assert bench.red_counts(cfg)["k_bwd_scatter_static"] == 128.0
+    ro, rd, _ = synthetic_sweep(7)
+    r = bench.red_counts(cfg, (ro, rd))
+    agg = int((cfg.static_grid().resolution <= bench.STATIC_AGG_RES).sum())
+    assert agg == 4 and r["k_bwd_scatter_static_algorithmic"] == 128.0
+    assert 128.0 - 8.0 * agg < r["k_bwd_scatter_static"] < 128.0          # runs exist, and no level disappears
+    # a ray that stays inside one cell for a whole warp issues 8 reductions per 32 samples at an aggregated level
+    still = (np.zeros((4, 3), np.float32), np.zeros((4, 3), np.float32))
+    assert abs(bench.red_counts(cfg, still)["k_bwd_scatter_static"] - (128.0 - 8.0 * agg * (1 - 1 / 32))) < 1e-6
+    # the macro the count mirrors
+    src = open(os.path.join(ROOT, "lidar4d_b200", "csrc", "l4d_split.cuh")).read()
+    assert f"#define L4D_STATIC_AGG_RES {bench.STATIC_AGG_RES}" in src
