@@ -183,7 +183,10 @@ int    l4d_adam_step(const L4DConfig* cfg, float* params, float* grads, float* e
 
 /* --- LiDAR_Renderer.run forward (renderer.py:44-140 + lidar4d.py:139-223), one fused kernel.
  *     depth[n], image[n,2] (ch0 raydrop, ch1 intensity), wsum[n]; weights/z_vals [n,S] optional.
- *     `saved` (l4d_saved_bytes) enables a later backward; NULL = inference. ------------------- */
+ *     `saved` (l4d_saved_bytes) enables a later backward; NULL = inference through the single kernel.
+ *     With `saved` the split pipeline runs: the buffer is also its exchange workspace and receives the
+ *     launch's contracted tables (dynamic hash x time constants of `frame`, time-plane rows) - the
+ *     backward must be called with the same saved / frame / rays / staged as its forward. -------- */
 size_t l4d_saved_bytes(const L4DConfig* cfg, uint32_t n_rays, uint32_t n_steps);
 int    l4d_render_forward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame,
                           const L4DRays* rays, float* depth, float* image, float* wsum,
@@ -192,8 +195,10 @@ int    l4d_render_forward(const L4DConfig* cfg, const void* staged, const L4DFra
 
 /* --- backward of the above: upstream grads g_depth[n], g_image[n,2], optional g_wsum[n],
  *     g_weights[n,S].  Hash-table gradients are accumulated straight into `grads`; plane and
- *     MLP gradients into `grad_work` (zero it first) and folded into `grads` by
- *     l4d_unstage_grads. ------------------------------------------------------------------- */
+ *     MLP gradients into `grad_work` (zero it ONCE after allocating it: every kernel that consumes a
+ *     region - l4d_unstage_grads, the fold kernels of the slice- / basis- / time-row-independent
+ *     accumulators it also holds - clears it again) and folded into `grads` by l4d_unstage_grads.
+ *     One grad_work per stream that runs backwards concurrently. ------------------------------ */
 size_t l4d_grad_work_bytes(const L4DConfig* cfg);
 int    l4d_render_backward(const L4DConfig* cfg, const void* staged, const L4DFrame* frame,
                            const L4DRays* rays, const void* saved, size_t saved_bytes,
