@@ -173,13 +173,18 @@ L4D_HD void l4d_bw_sigma_c(const DevModel& M, const BwSample& s, const float* fe
 // (a RED.F32x4 counts as 4) and plane gradients are half of all atomics of the backward, so each run
 // is summed with a segmented warp scan and only its last lane issues the REDs.
 #if defined(__CUDACC__)
+// warp-collective helpers: device code.  tests/hostsim/warpsim.cu (test infrastructure) compiles them for the host with the warp
+// intrinsics redirected to a 32-thread lockstep emulator, which is why the qualifier is a macro.
+#ifndef L4D_WARP_FN
+#define L4D_WARP_FN __device__ __forceinline__
+#endif
 struct WarpRuns {
   int dist;       // lane - first lane of this lane's run of equal keys
   int maxdist;    // longest run of the warp - 1 (warp-uniform): the scans stop after ceil(log2(maxdist+1)) steps
   bool tail;      // last lane of its run
   unsigned mask;  // the lanes of this lane's run
 };
-__device__ __forceinline__ WarpRuns l4d_warp_runs(int key) {
+L4D_WARP_FN WarpRuns l4d_warp_runs(int key) {
   const unsigned lane = threadIdx.x & 31u;
   const int prev = __shfl_up_sync(0xffffffffu, key, 1);
   const bool head = (lane == 0u) || (prev != key);
@@ -200,7 +205,7 @@ __device__ __forceinline__ WarpRuns l4d_warp_runs(int key) {
 #ifndef L4D_SCAN_FMA
 #define L4D_SCAN_FMA 1
 #endif
-__device__ __forceinline__ void l4d_seg_sum8(float (&v)[8], const WarpRuns& r) {
+L4D_WARP_FN void l4d_seg_sum8(float (&v)[8], const WarpRuns& r) {
   // only as many steps as the longest run of the warp needs (measured against a fixed 5-step scan: 14.2 -> 11.8 ms)
 #pragma unroll 1
   for (int d = 1; d <= r.maxdist; d <<= 1) {
@@ -231,7 +236,7 @@ __device__ __forceinline__ void l4d_seg_sum8(float (&v)[8], const WarpRuns& r) {
 #define L4D_RUNSUM_REDUX 0
 #endif
 template <int N>
-__device__ __forceinline__ void l4d_run_sum(float (&v)[N], const WarpRuns& r) {
+L4D_WARP_FN void l4d_run_sum(float (&v)[N], const WarpRuns& r) {
   if (r.maxdist == 0) return;                       // warp-uniform: every lane is its own run
   float am = 0.f;
 #pragma unroll
@@ -247,7 +252,7 @@ __device__ __forceinline__ void l4d_run_sum(float (&v)[N], const WarpRuns& r) {
   }
 }
 // all 32 lanes must call; g may be zero for lanes without a contribution
-__device__ __forceinline__ void l4d_plane_scatter_warp(float* G, int W, const Bilerp& b, const float g[8]) {
+L4D_WARP_FN void l4d_plane_scatter_warp(float* G, int W, const Bilerp& b, const float g[8]) {
   const WarpRuns r = l4d_warp_runs(b.y0 * W + b.x0);
   const float wgt[4] = {b.wx0 * b.wy0, b.wx1 * b.wy0, b.wx0 * b.wy1, b.wx1 * b.wy1};
   const int xs[4] = {b.x0, b.x1, b.x0, b.x1};
@@ -270,7 +275,7 @@ __device__ __forceinline__ void l4d_plane_scatter_warp(float* G, int W, const Bi
   }
 }
 // time planes: the y (time) weights are the same for every lane, so two sums per channel suffice
-__device__ __forceinline__ void l4d_plane_scatter_warp_t(float* G, int W, const Bilerp& b, const float g[8]) {
+L4D_WARP_FN void l4d_plane_scatter_warp_t(float* G, int W, const Bilerp& b, const float g[8]) {
   const WarpRuns r = l4d_warp_runs(b.x0);
   float s0[8], s1[8];
 #pragma unroll
@@ -301,7 +306,7 @@ __device__ __forceinline__ void l4d_plane_scatter_warp_t(float* G, int W, const 
 }
 // gradient rows of the contracted time planes (DevGrads::pl_rows): the same run sums, and the tail lane only issues the two
 // texels of the row - the time-row weights are applied once per launch by k_fold_planes
-__device__ __forceinline__ void l4d_row_scatter_warp(float* Grow, const Bilerp& b, const float g[8]) {
+L4D_WARP_FN void l4d_row_scatter_warp(float* Grow, const Bilerp& b, const float g[8]) {
   const WarpRuns r = l4d_warp_runs(b.x0);
   float s0[8], s1[8];
 #pragma unroll
@@ -320,6 +325,27 @@ __device__ __forceinline__ void l4d_row_scatter_warp(float* Grow, const Bilerp& 
     l4d_red4(p0 + 4, s0[4], s0[5], s0[6], s0[7]);
     l4d_red4(p1, s1[0], s1[1], s1[2], s1[3]);
     l4d_red4(p1 + 4, s1[4], s1[5], s1[6], s1[7]);
+  }
+}
+// one level of the static hash for a warp of consecutive samples: runs of lanes with equal `key` (= equal cells, hence equal
+// corner indices) are summed and the last lane of a run issues the 8 corner reductions; two passes of 4 corners x 4 features keep
+// 16 values live.  All 32 lanes must call; lanes without a sample pass dd = 0.
+L4D_WARP_FN void l4d_static_scatter_warp(float* gbase, const uint32_t (&idx)[8], const float (&w)[8], const float4 dd, int key) {
+  const WarpRuns r = l4d_warp_runs(key);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float s0[8], s1[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      s0[2 * c] = w[4 * h + c] * dd.x; s0[2 * c + 1] = w[4 * h + c] * dd.y;
+      s1[2 * c] = w[4 * h + c] * dd.z; s1[2 * c + 1] = w[4 * h + c] * dd.w;
+    }
+    l4d_seg_sum8(s0, r);
+    l4d_seg_sum8(s1, r);
+    if (r.tail) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) l4d_red4(gbase + (size_t)idx[4 * h + c] * 4, s0[2 * c], s0[2 * c + 1], s1[2 * c], s1[2 * c + 1]);
+    }
   }
 }
 #endif

@@ -509,22 +509,7 @@ __global__ void __launch_bounds__(NT, L4D_STATIC_AGG_RES ? 5 : 8) k_bwd_scatter_
         const float sc = M.gs.scale[l];
         l4d_pos_fract(sc, x, cx, fx); l4d_pos_fract(sc, y, cy, fy); l4d_pos_fract(sc, z, cz, fz);
         // equal keys <=> equal cells for neighbouring lanes (their linear cell indices differ by far less than 2^32)
-        const WarpRuns r = l4d_warp_runs((int)(cx + M.gs.res[l] * (cy + M.gs.res[l] * cz)));
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {        // two passes of 4 corners x 4 features keep 16 values live
-          float s0[8], s1[8];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            s0[2 * c] = w[4 * h + c] * dd.x; s0[2 * c + 1] = w[4 * h + c] * dd.y;
-            s1[2 * c] = w[4 * h + c] * dd.z; s1[2 * c + 1] = w[4 * h + c] * dd.w;
-          }
-          l4d_seg_sum8(s0, r);
-          l4d_seg_sum8(s1, r);
-          if (r.tail) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) l4d_red4(gbase + (size_t)idx[4 * h + c] * 4, s0[2 * c], s0[2 * c + 1], s1[2 * c], s1[2 * c + 1]);
-          }
-        }
+        l4d_static_scatter_warp(gbase, idx, w, dd, (int)(cx + M.gs.res[l] * (cy + M.gs.res[l] * cz)));
         continue;
       }
 #endif

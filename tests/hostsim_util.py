@@ -28,6 +28,21 @@ def build(force=False):
     return SO
 
 
+WS_SRC = os.path.join(HERE, "hostsim", "warpsim.cu")
+WS_SO = os.path.join(HERE, "hostsim", "_warpsim.so")
+
+
+def build_warpsim(force=False):
+    """tests/hostsim/warpsim.cu: the warp-collective gradient sinks compiled for the CPU on a 32-thread lockstep emulator."""
+    deps = [WS_SRC] + [os.path.join(HERE, "..", "lidar4d_b200", "csrc", f) for f in ("l4d_core.cuh", "l4d_bwd.cuh")]
+    if not force and os.path.exists(WS_SO) and all(os.path.getmtime(WS_SO) >= os.path.getmtime(d) for d in deps):
+        return WS_SO
+    cmd = ["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off",
+           "-gencode", "arch=compute_100a,code=sm_100a", "-o", WS_SO, WS_SRC, "-lpthread"]
+    subprocess.run(cmd, check=True)
+    return WS_SO
+
+
 def lib():
     global _LIB
     if _LIB is None:
